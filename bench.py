@@ -1,0 +1,456 @@
+#!/usr/bin/env python
+"""bench.py -- MSDA forward+backward throughput on B200, with roofline, CPU baseline and end-to-end numbers.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]          # our arm (N>1: launched by torch.distributed.run)
+    python bench.py --impl reference [...]                        # the reference's CPU route on the host cores
+
+Workload (BASELINE.json configs[1], the configuration the reference's published numbers are quoted on,
+scripts/benchmark.py:25-31): B=4 images per GPU, Q=10 000 queries, H=8, D=32, L=4 (64^2,32^2,16^2,8^2), K=4, fp32,
+padding_mode="border", align_corners=True, synthetic seeded inputs (img~N(0,1), points~U[0,1), weights=softmax(N(0,1))
+over K, grad_out~U[0,1)).  One STEP = one forward + one backward (all three gradients) over that batch.
+Multi-GPU: the path shards by batch with no data-path collective, every rank owns B=4 images -> weak
+scaling; value = all ranks' queries / max-over-ranks device time.
+
+Timing: every step is bracketed by CUDA events on the launching stream; a 256 MiB buffer is overwritten between
+steps OUTSIDE the event pair so each step starts with a cold L2 (the reference's do_bench does the same).  The K steps
+as a whole are bracketed by barrier + torch.cuda.synchronize().
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+for _p in (ROOT, ROOT / "msda-triton_b200"):
+    if str(_p) not in sys.path:
+        sys.path.insert(0, str(_p))
+
+import torch  # noqa: E402
+
+BENCH_PYRAMID = [(64, 64), (32, 32), (16, 16), (8, 8)]
+DETR_PYRAMID = [(100, 167), (50, 84), (25, 42), (13, 21)]
+WORKLOADS = {
+    # name: (B, Q, H, D, pyramid, K, padding, align)
+    "bench_q10k_border": (4, 10000, 8, 32, BENCH_PYRAMID, 4, "border", True),
+    "bench_q10k_zeros": (4, 10000, 8, 32, BENCH_PYRAMID, 4, "zeros", False),
+    "detr_encoder_zeros": (2, 22223, 8, 32, DETR_PYRAMID, 4, "zeros", False),
+}
+HEADLINE = "bench_q10k_border"
+METRIC = "MSDA fwd+bwd throughput, 10k-query benchmark shape (fp32)"
+UNIT = "queries/s"
+
+
+def make_inputs(name, seed, device="cpu", pin=False):
+    B, Q, H, D, pyr, K, pm, ac = WORKLOADS[name]
+    g = torch.Generator().manual_seed(seed)
+    L = len(pyr)
+    npix = sum(h * w for h, w in pyr)
+    t = {
+        "img": torch.randn(B, npix, H, D, generator=g),
+        "pts": torch.rand(B, Q, H, L, K, 2, generator=g),
+        "aw": torch.softmax(torch.randn(B, Q, H, L, K, generator=g), dim=-1),
+        "go": torch.rand(B, Q, H, D, generator=g),
+    }
+    shapes = torch.tensor(pyr, dtype=torch.int64)
+    if pin:
+        t = {k: v.pin_memory() for k, v in t.items()}
+    elif device != "cpu":
+        t = {k: v.to(device) for k, v in t.items()}
+        shapes = shapes.to(device)
+    return t, shapes
+
+
+def byte_model(name, unique_rows=None):
+    """Algorithmic bytes (SURVEY.md 8d / BASELINE.md 3), fp32."""
+    B, Q, H, D, pyr, K, _, _ = WORKLOADS[name]
+    L, e = len(pyr), 4
+    npix = sum(h * w for h, w in pyr)
+    V = B * npix * H * D * e
+    U = V if unique_rows is None else unique_rows * D * e
+    S = B * Q * H * L * K * 2 * e
+    A = B * Q * H * L * K * e
+    O = B * Q * H * D * e  # noqa: E741
+    G = B * Q * H * L * K * 4 * D * e
+    return {"fwd": U + S + A + O, "bwd": (O + U + S + A) + (V + S + A), "gather": G, "V": V, "U": U}
+
+
+def count_unique_rows(name, t, shapes):
+    """Distinct (b, pixel, h) rows the bilinear corners touch (torch ops, setup only; not on any timed path)."""
+    B, Q, H, D, pyr, K, pm, ac = WORKLOADS[name]
+    pts = t["pts"].double()
+    dev = pts.device
+    npix = sum(h * w for h, w in pyr)
+    hw = torch.tensor(pyr, dtype=torch.float64, device=dev)
+    wh = hw.flip(-1)[None, None, None, :, None, :]
+    xy = pts * (wh - 1) if ac else pts * wh - 0.5
+    x0 = xy.floor()
+    offs = torch.tensor([0] + [h * w for h, w in pyr[:-1]], device=dev).cumsum(0)[None, None, None, :, None]
+    wi = hw[:, 1].long()[None, None, None, :, None]
+    hi = hw[:, 0].long()[None, None, None, :, None]
+    b = torch.arange(B, device=dev)[:, None, None, None, None]
+    h = torch.arange(H, device=dev)[None, None, :, None, None]
+    keys = []
+    for dy in (0, 1):
+        for dx in (0, 1):
+            xi = (x0[..., 0].long() + dx)
+            yi = (x0[..., 1].long() + dy)
+            valid = (xi >= 0) & (xi < wi) & (yi >= 0) & (yi < hi)
+            xi = xi.clamp(min=0).minimum(wi - 1)
+            yi = yi.clamp(min=0).minimum(hi - 1)
+            key = (b * npix + offs + yi * wi + xi) * H + h
+            keys.append(key[valid] if pm == "zeros" else key.reshape(-1))
+    return int(torch.unique(torch.cat(keys)).numel())
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU during the timed region (NVML)."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def _poll(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.005)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._poll, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def physical_gpu_index(local_index):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_index])
+        except Exception:  # noqa: BLE001
+            return local_index
+    return local_index
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU route (torch grid_sample per level) on the host cores
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_route_sample(name, reps, warm=1):
+    """Times fwd+bwd of the reference's native-torch route (port: oracle/grid_sample_port.py of frontend.py:15-68)
+    on ONE image (B=1) of the workload with all host threads; returns (queries/s, ms per image, threads, sample)."""
+    from oracle import grid_sample_port as port
+    B, Q, H, D, pyr, K, pm, ac = WORKLOADS[name]
+    t, shapes = make_inputs(name, seed=0)
+    one = {k: v[:1].contiguous() for k, v in t.items()}
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    times = []
+    for i in range(warm + reps):
+        t0 = time.perf_counter()
+        port.forward_backward(one["img"], shapes, one["pts"], one["aw"], one["go"], pm, ac)
+        dt = time.perf_counter() - t0
+        if i >= warm:
+            times.append(dt)
+    times.sort()
+    med = times[len(times) // 2]
+    return Q / med, med * 1e3, torch.get_num_threads(), f"fwd+bwd of 1 of the {B} images (B=1, Q={Q}), median of {reps}"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B, Q, H, D, pyr, K, pm, ac = WORKLOADS[HEADLINE]
+    qps, ms_img, threads, sample = cpu_route_sample(HEADLINE, reps=max(1, args.steps), warm=max(1, args.warmup))
+    line = {
+        "impl": "reference",
+        "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_img * B, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{HEADLINE}: B={B} Q={Q} H={H} D={D} L={len(pyr)} K={K} pyramid=64^2..8^2 "
+                               f"{pm}/align_corners={ac}, fwd+bwd", "l2": "n/a (CPU)",
+                   "note": "each step = a bounded sample: 1 of the B images; ms_per_step is scaled to the full batch"},
+        "cpu_baseline": {"value": qps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------------------
+def time_workload(name, steps, warmup, K, flush, dist_sync=None, clock_index=None):
+    """Returns dict with per-step mean ms for fwd, bwd, total (device events, cold L2)."""
+    B, Q, H, D, pyr, Kp, pm, ac = WORKLOADS[name]
+    t, shapes = make_inputs(name, seed=0, device="cuda")
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+
+    def one_step(e=None):
+        flush.fill_(1.0)                      # cold L2: 256 MiB written between steps, outside the event pair
+        if e:
+            e[0].record()
+        out = K.b200_multi_scale_deformable_attention_fwd(t["img"], shapes, t["pts"], t["aw"], pm, ac)
+        if e:
+            e[1].record()
+        grads = K.b200_multi_scale_deformable_attention_bwd(t["go"], t["img"], shapes, t["pts"], t["aw"], pm, ac)
+        if e:
+            e[2].record()
+        return out, grads
+
+    for _ in range(warmup):
+        one_step()
+    sampler = ClockSampler(clock_index) if clock_index is not None else None
+    if dist_sync:
+        dist_sync()
+    torch.cuda.synchronize()
+    wall0 = time.perf_counter()
+    if sampler:
+        sampler.__enter__()
+    for i in range(steps):
+        one_step(ev[i])
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.__exit__()
+    if dist_sync:
+        dist_sync()
+    wall = time.perf_counter() - wall0
+    fwd = sum(e[0].elapsed_time(e[1]) for e in ev) / steps
+    bwd = sum(e[1].elapsed_time(e[2]) for e in ev) / steps
+    res = {"fwd_ms": fwd, "bwd_ms": bwd, "step_ms": fwd + bwd, "wall_s": wall,
+           "clocks": sampler.summary() if sampler else None}
+    res["unique_rows"] = count_unique_rows(name, t, shapes)
+    return res
+
+
+def time_e2e(name, steps, warmup, dist_sync=None):
+    """Public API, host buffers: H2D of the step's inputs from pinned memory, fwd + autograd bwd, D2H of out and the
+    three gradients -- all inside the timed region."""
+    import msda_triton
+    B, Q, H, D, pyr, Kp, pm, ac = WORKLOADS[name]
+    host, shapes = make_inputs(name, seed=0, pin=True)
+    shapes_dev = shapes.cuda()
+    h_out = torch.empty(B, Q, H, D).pin_memory()
+    h_gi = torch.empty_like(host["img"]).pin_memory()
+    h_gp = torch.empty_like(host["pts"]).pin_memory()
+    h_ga = torch.empty_like(host["aw"]).pin_memory()
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = sum(v.numel() * v.element_size() for v in (h_out, h_gi, h_gp, h_ga))
+
+    def one_step():
+        img = host["img"].to("cuda", non_blocking=True).requires_grad_(True)
+        pts = host["pts"].to("cuda", non_blocking=True).requires_grad_(True)
+        aw = host["aw"].to("cuda", non_blocking=True).requires_grad_(True)
+        go = host["go"].to("cuda", non_blocking=True)
+        out = msda_triton.multiscale_deformable_attention(img, shapes_dev, pts, aw, pm, ac)
+        out.backward(go)
+        h_out.copy_(out.detach(), non_blocking=True)
+        h_gi.copy_(img.grad, non_blocking=True)
+        h_gp.copy_(pts.grad, non_blocking=True)
+        h_ga.copy_(aw.grad, non_blocking=True)
+
+    for _ in range(warmup):
+        one_step()
+    if dist_sync:
+        dist_sync()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one_step()
+    e1.record()
+    torch.cuda.synchronize()
+    if dist_sync:
+        dist_sync()
+    return e0.elapsed_time(e1) / steps, h2d, d2h
+
+
+def l2_probe(K_lib):
+    """Random 128-byte-row gather / red.add.v4 throughput over an L2-resident 32 MiB buffer (the access shape of the
+    kernels) -- the 'L2 gather roof' SURVEY.md 8d asks to measure next to every result."""
+    import ctypes
+    lib = K_lib
+    rows_buf = (32 << 20) // 128
+    buf = torch.zeros(rows_buf * 32, device="cuda")
+    sink = torch.zeros(4, device="cuda")
+    n = 64 * 1024 * 1024 // 8   # 8.4M rows = 1 GiB of row traffic
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    res = {}
+    for kind in ("gather", "scatter"):
+        def launch(seed):
+            if kind == "gather":
+                return lib.msda_probe_gather(ctypes.c_void_p(sink.data_ptr()), ctypes.c_void_p(buf.data_ptr()),
+                                             rows_buf, n, seed, st)
+            return lib.msda_probe_scatter(ctypes.c_void_p(buf.data_ptr()), rows_buf, n, seed, st)
+        for s in range(3):
+            assert launch(s) == 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(5):
+            launch(10 + s)
+        e1.record()
+        torch.cuda.synchronize()
+        res[kind + "_gbs"] = n * 128 / (e0.elapsed_time(e1) / 5 * 1e-3) / 1e9
+    return res
+
+
+def run_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the MSDA path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from msda_triton import _lib, kernels as K
+
+    def sync():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    flush = torch.empty(256 << 18, device="cuda")  # 256 MiB of fp32
+    B, Q, H, D, pyr, Kp, pm, ac = WORKLOADS[HEADLINE]
+
+    head = time_workload(HEADLINE, args.steps, args.warmup, K, flush, dist_sync=sync,
+                         clock_index=physical_gpu_index(local))
+    e2e_ms, h2d, d2h = time_e2e(HEADLINE, max(3, min(args.steps, 20)), 3, dist_sync=sync)
+
+    # max over ranks of the device time
+    tmax = torch.tensor([head["step_ms"], head["fwd_ms"], head["bwd_ms"], e2e_ms], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    step_ms, fwd_ms, bwd_ms, e2e_ms = tmax.tolist()
+
+    extra = {}
+    cpu = None
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        bm = byte_model(HEADLINE, head["unique_rows"])
+        traffic = None
+        tr = ROOT / "profiles" / "traffic.json"
+        if tr.exists():
+            try:
+                traffic = json.loads(tr.read_text()).get("msda_bwd", {}).get("dram_bytes_per_launch")
+            except Exception:  # noqa: BLE001
+                traffic = None
+        ach = bm["bwd"] / (bwd_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "msda_bwd (backward pass incl. its grad_img zero-fill)",
+                    "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": traffic, "algorithmic_bytes": bm["bwd"],
+                    "fwd": {"achieved": bm["fwd"] / (fwd_ms * 1e-3) / 1e9, "algorithmic_bytes": bm["fwd"],
+                            "frac": bm["fwd"] / (fwd_ms * 1e-3) / 1e9 / peak},
+                    "gather_traffic_bytes": bm["gather"],
+                    "gather_gbs": {"fwd": bm["gather"] / (fwd_ms * 1e-3) / 1e9,
+                                   "bwd_read_plus_atomic": 2 * bm["gather"] / (bwd_ms * 1e-3) / 1e9}}
+        if world == 1 and not args.quick:
+            try:
+                extra["l2_probe"] = l2_probe(_lib.get_lib())
+            except Exception as ex:  # noqa: BLE001
+                extra["l2_probe"] = {"error": str(ex)}
+            for name in WORKLOADS:
+                if name == HEADLINE:
+                    continue
+                r = time_workload(name, max(5, args.steps // 4), 3, K, flush)
+                bmn = byte_model(name, r["unique_rows"])
+                extra[name] = {"fwd_ms": r["fwd_ms"], "bwd_ms": r["bwd_ms"], "fwd_bwd_ms": r["step_ms"],
+                               "fwd_hbm_frac": bmn["fwd"] / (r["fwd_ms"] * 1e-3) / 1e9 / peak,
+                               "bwd_hbm_frac": bmn["bwd"] / (r["bwd_ms"] * 1e-3) / 1e9 / peak,
+                               "fwd_gather_gbs": bmn["gather"] / (r["fwd_ms"] * 1e-3) / 1e9}
+            qps, ms_img, threads, sample = cpu_route_sample(HEADLINE, reps=10, warm=1)
+            cpu = {"value": qps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                   "ms_per_image": ms_img}
+        line = {
+            "metric": METRIC, "value": world * B * Q / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{HEADLINE}: B={B}/GPU Q={Q} H={H} D={D} L={len(pyr)} K={Kp} pyramid=64^2..8^2 "
+                                   f"{pm}/align_corners={ac}, fwd+bwd (all 3 grads)",
+                       "l2": "flushed between steps (256 MiB overwrite outside the event pair)",
+                       "parallelism": f"batch-sharded x{world}, no collective"},
+            "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
+            "clocks": head["clocks"],
+            "e2e": {"value": world * B * Q / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": 2 * args.steps,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "extra": extra,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--quick", action="store_true", help="headline only: skip extra workloads, probes, cpu baseline")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,136 @@
+/*
+ * msda_b200.h -- C ABI of libmsda_b200.so: multiscale deformable attention (MSDA) for NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary for the reference's kernel layer.  The reference (rziga/msda-triton) has exactly two
+ * operator entry points, both Python functions that launch Triton kernels:
+ *
+ *   triton_multi_scale_deformable_attention_fwd   src/msda_triton/kernels.py:351-379   -> msda_forward
+ *   triton_multi_scale_deformable_attention_bwd   src/msda_triton/kernels.py:556-592   -> msda_backward
+ *
+ * and one piece of device-side preprocessing that every Triton program repeats:
+ *
+ *   load_shapes_and_level_offsets                 src/msda_triton/kernels.py:44-64     -> done inside the kernels
+ *                                                                                         (once per CTA), and exposed
+ *                                                                                         as msda_level_table
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers on the current CUDA device (including img_shapes, like the reference, which
+ *     reads the [L,2] int64 (h,w) table on device and never syncs: frontend.py:93-95, kernels.py:52-56).
+ *   - All tensors are dense row-major ("contiguous") in the reference's layouts:
+ *       img   [B, Npix, H, D]       Npix = sum_l h_l*w_l        (frontend.py:157)
+ *       img_shapes [L, 2] int64, (h, w) order                     (frontend.py:158)
+ *       sampling_points [B, Q, H, L, K, 2], (x, y) in [0,1]       (frontend.py:159)
+ *       attention_weights [B, Q, H, L, K]                         (frontend.py:160)
+ *       out / grad_out [B, Q, H, D]                               (frontend.py:165)
+ *   - The caller owns every buffer.  The library never allocates device memory, never synchronises, and launches only
+ *     on the stream it is given (cudaStream_t passed as void*; NULL = legacy default stream).  All entry points are
+ *     therefore CUDA-graph capturable.
+ *   - Return value: 0 on success, a negative MSDA_ERR_* code on invalid arguments, a positive cudaError_t value if
+ *     a CUDA call failed.  msda_last_error() returns a thread-local, human-readable description of the last failure.
+ *   - Thread safety: the library is stateless apart from the thread-local error string and a per-device cache of
+ *     immutable device properties; it may be called concurrently from several host threads (autograd calls backward
+ *     from its own thread).
+ */
+#ifndef MSDA_B200_H_
+#define MSDA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSDA_B200_ABI_VERSION 1
+
+/* storage dtype of img / sampling_points / attention_weights / out (all four share it) */
+enum msda_dtype {
+    MSDA_DTYPE_F32 = 0,  /* compute + accumulate fp32 */
+    MSDA_DTYPE_F16 = 1,  /* fp16 storage, fp32 compute + accumulate */
+    MSDA_DTYPE_BF16 = 2, /* bf16 storage, fp32 compute + accumulate (the reference rejects bf16: kernels.py:40-41) */
+    MSDA_DTYPE_F64 = 3   /* compute + accumulate fp64 */
+};
+
+/* reference: padding_mode Literal["border","zeros"] (frontend.py:150) */
+enum msda_padding { MSDA_PAD_ZEROS = 0, MSDA_PAD_BORDER = 1 };
+
+/* msda_backward flags */
+enum msda_bwd_flags {
+    MSDA_BWD_NEED_IMG = 1,      /* produce grad_img            (ctx.needs_input_grad[0]) */
+    MSDA_BWD_NEED_POINTS = 2,   /* produce grad_sampling_points (ctx.needs_input_grad[2]) */
+    MSDA_BWD_NEED_WEIGHTS = 4,  /* produce grad_attention_weights (ctx.needs_input_grad[3]) */
+    MSDA_BWD_NEED_ALL = 7,
+    MSDA_BWD_DETERMINISTIC = 8  /* grad_img by sorted-segment reduction instead of atomics (bit-reproducible) */
+};
+
+enum msda_error {
+    MSDA_OK = 0,
+    MSDA_ERR_NULL_POINTER = -1,
+    MSDA_ERR_BAD_DTYPE = -2,
+    MSDA_ERR_BAD_SHAPE = -3,
+    MSDA_ERR_BAD_MODE = -4,
+    MSDA_ERR_WORKSPACE = -5,
+    MSDA_ERR_UNSUPPORTED_DEVICE = -6
+};
+
+/* Problem description shared by every entry point (sizes follow BASELINE.json naming). */
+typedef struct msda_problem {
+    int64_t B;    /* batch */
+    int64_t Npix; /* total pyramid pixels, sum_l h_l*w_l */
+    int64_t H;    /* heads */
+    int64_t D;    /* channels per head */
+    int64_t Q;    /* queries */
+    int64_t L;    /* pyramid levels */
+    int64_t K;    /* sampling points per level */
+    int32_t dtype;         /* enum msda_dtype */
+    int32_t padding_mode;  /* enum msda_padding */
+    int32_t align_corners; /* 0 / 1 */
+    int32_t reserved;      /* must be 0 */
+} msda_problem;
+
+int msda_abi_version(void);
+const char *msda_last_error(void);
+
+/*
+ * Forward: out[b,q,h,:] = sum_{l,k} w[b,q,h,l,k] * bilinear(img_l[b,:,h,:], p[b,q,h,l,k])
+ * Replaces kernels.py:351-379 (wrapper) + :267-348 (kernel) + :120-252 (sample_bilinear).
+ */
+int msda_forward(void *out, const void *img, const int64_t *img_shapes, const void *sampling_points,
+                 const void *attention_weights, const msda_problem *prob, void *stream);
+
+/*
+ * Bytes of scratch msda_backward needs for `prob` and `flags` (0 if none).
+ *   - fp16/bf16 storage: grad_img is accumulated in an fp32 image of B*Npix*H*D floats, then rounded once.
+ *   - MSDA_BWD_DETERMINISTIC: sort keys/values + segment scratch.
+ */
+size_t msda_backward_workspace_bytes(const msda_problem *prob, int flags);
+
+/*
+ * Backward: grads of out w.r.t. img (scatter-add), sampling_points (w.r.t. the normalised [0,1] coordinate) and
+ * attention_weights, computed in ONE pass that also recomputes the forward sampling.
+ * Replaces kernels.py:556-592 (wrapper, incl. its three zero-fills) + :396-553 (kernel).
+ * grad_img is zero-filled by the library on `stream`; grad_points / grad_weights are fully overwritten.
+ * Pointers whose MSDA_BWD_NEED_* bit is clear may be NULL.
+ */
+int msda_backward(void *grad_img, void *grad_points, void *grad_weights, const void *grad_out, const void *img,
+                  const int64_t *img_shapes, const void *sampling_points, const void *attention_weights,
+                  const msda_problem *prob, int flags, void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * Device-side level preprocessing (kernels.py:44-64): table[l] = {h_l, w_l, offset_l, 0} as int32, plus
+ * table[L] = {sum_l h_l*w_l, Npix, sum==Npix, 0} so a caller can validate asynchronously.  table: (L+1)*4 int32.
+ */
+int msda_level_table(int32_t *table, const int64_t *img_shapes, int64_t L, int64_t Npix, void *stream);
+
+/*
+ * Measurement helpers for the L2 gather / atomic roof (SURVEY.md section 8d "L2_peak must be measured on the box").
+ * Each launch issues `rows` independent random 128-byte row reads (or red.global.add.v4.f32 row adds) over a
+ * buffer of `buf_rows` rows of 128 B, one 8-lane group per row, the same access shape the MSDA kernels use.
+ */
+int msda_probe_gather(float *sink, const float *buf, int64_t buf_rows, int64_t rows, uint32_t seed, void *stream);
+int msda_probe_scatter(float *buf, int64_t buf_rows, int64_t rows, uint32_t seed, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSDA_B200_H_ */

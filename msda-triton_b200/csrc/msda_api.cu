@@ -1,0 +1,360 @@
+// msda_api.cu -- the extern "C" surface of libmsda_b200.so (declared in include/msda_b200.h).
+//
+// Validation, kernel selection and launch only: no allocation, no synchronisation, no default-stream use.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/msda_b200.h"
+#include "msda_common.cuh"
+#include "msda_launch.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int fail_cuda(cudaError_t e, const char *what) {
+    snprintf(g_err, sizeof(g_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    return (int)e;
+}
+
+// Immutable per-device facts, looked up once.
+struct DeviceInfo {
+    int sm_count = 0;
+    int cc_major = 0;
+};
+DeviceInfo g_dev[64];
+std::once_flag g_dev_once[64];
+
+int device_info(DeviceInfo *out) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaGetDevice");
+    if (dev < 0 || dev >= 64) return fail(MSDA_ERR_UNSUPPORTED_DEVICE, "device ordinal %d out of range", dev);
+    std::call_once(g_dev_once[dev], [dev]() {
+        cudaDeviceGetAttribute(&g_dev[dev].sm_count, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&g_dev[dev].cc_major, cudaDevAttrComputeCapabilityMajor, dev);
+    });
+    *out = g_dev[dev];
+    if (out->cc_major != 10)
+        return fail(MSDA_ERR_UNSUPPORTED_DEVICE,
+                    "libmsda_b200 is built for sm_100a only; current device has compute capability major %d",
+                    out->cc_major);
+    return MSDA_OK;
+}
+
+size_t dtype_size(int dtype) {
+    switch (dtype) {
+        case MSDA_DTYPE_F32: return 4;
+        case MSDA_DTYPE_F16: return 2;
+        case MSDA_DTYPE_BF16: return 2;
+        case MSDA_DTYPE_F64: return 8;
+    }
+    return 0;
+}
+
+int validate(const msda_problem *p) {
+    if (!p) return fail(MSDA_ERR_NULL_POINTER, "msda_problem is NULL");
+    if (dtype_size(p->dtype) == 0) return fail(MSDA_ERR_BAD_DTYPE, "unknown dtype code %d", p->dtype);
+    if (p->padding_mode != MSDA_PAD_ZEROS && p->padding_mode != MSDA_PAD_BORDER)
+        return fail(MSDA_ERR_BAD_MODE, "padding_mode must be MSDA_PAD_ZEROS or MSDA_PAD_BORDER, got %d", p->padding_mode);
+    if (p->align_corners != 0 && p->align_corners != 1)
+        return fail(MSDA_ERR_BAD_MODE, "align_corners must be 0 or 1, got %d", p->align_corners);
+    if (p->B < 0 || p->Q < 0 || p->H <= 0 || p->D <= 0 || p->L <= 0 || p->K <= 0 || p->Npix <= 0)
+        return fail(MSDA_ERR_BAD_SHAPE, "invalid sizes B=%lld Npix=%lld H=%lld D=%lld Q=%lld L=%lld K=%lld",
+                    (long long)p->B, (long long)p->Npix, (long long)p->H, (long long)p->D, (long long)p->Q,
+                    (long long)p->L, (long long)p->K);
+    const long long kInt = 0x7fffffffLL;
+    if (p->Npix > kInt || p->Q > kInt || p->H > kInt || p->D > kInt || p->B > kInt || p->L * p->K > (1 << 20) ||
+        p->L > 2048)
+        return fail(MSDA_ERR_BAD_SHAPE, "a dimension exceeds the supported range (each < 2^31, L <= 2048, L*K <= 2^20)");
+    if (p->Npix * p->H * p->D > (1LL << 46))
+        return fail(MSDA_ERR_BAD_SHAPE, "one image of the pyramid is too large");
+    return MSDA_OK;
+}
+
+bool aligned(const void *p, size_t a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+// Largest power-of-two vector width (elements) such that D % vec == 0, vec*sizeof(T) <= 16 and every row pointer
+// is aligned to it.
+int pick_vec(const msda_problem *p, std::initializer_list<const void *> row_ptrs) {
+    const size_t es = dtype_size(p->dtype);
+    int vec = (int)(16 / es);
+    while (vec > 1) {
+        bool ok = (p->D % vec) == 0;
+        for (const void *q : row_ptrs) ok = ok && aligned(q, vec * es);
+        if (ok) break;
+        vec >>= 1;
+    }
+    return vec;
+}
+
+void fill_args(msda::KernelArgs &a, const msda_problem *p, int vec) {
+    std::memset(&a, 0, sizeof(a));
+    a.B = (int)p->B;
+    a.Q = (int)p->Q;
+    a.H = (int)p->H;
+    a.D = (int)p->D;
+    a.L = (int)p->L;
+    a.K = (int)p->K;
+    a.Npix = (int)p->Npix;
+    a.LK = (int)(p->L * p->K);
+    a.units = p->B * p->Q * p->H;
+    a.border = p->padding_mode == MSDA_PAD_BORDER;
+    a.align = p->align_corners;
+    const int need = (int)((p->D + vec - 1) / vec);  // lanes needed to cover D once
+    int lanes = 1;
+    while (lanes < need && lanes < 32) lanes <<= 1;
+    a.lanes = lanes;
+    a.chunks = (need + lanes - 1) / lanes;
+}
+
+// Debug / test switch: MSDA_B200_FORCE_GENERIC=1 routes every problem to the generic kernels.
+bool force_generic() {
+    const char *e = std::getenv("MSDA_B200_FORCE_GENERIC");
+    return e && e[0] && e[0] != '0';
+}
+
+}  // namespace
+
+extern "C" {
+
+int msda_abi_version(void) { return MSDA_B200_ABI_VERSION; }
+
+const char *msda_last_error(void) { return g_err; }
+
+int msda_forward(void *out, const void *img, const int64_t *img_shapes, const void *sampling_points,
+                 const void *attention_weights, const msda_problem *prob, void *stream) {
+    int rc = validate(prob);
+    if (rc != MSDA_OK) return rc;
+    if (prob->B == 0 || prob->Q == 0) return MSDA_OK;
+    if (!out || !img || !img_shapes || !sampling_points || !attention_weights)
+        return fail(MSDA_ERR_NULL_POINTER, "msda_forward: NULL device pointer");
+    const size_t es = dtype_size(prob->dtype);
+    if (!aligned(sampling_points, 2 * es) || !aligned(attention_weights, es) || !aligned(img_shapes, 8))
+        return fail(MSDA_ERR_BAD_SHAPE, "msda_forward: sampling_points must be aligned to one (x,y) pair");
+    DeviceInfo dev;
+    rc = device_info(&dev);
+    if (rc != MSDA_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+    const int vec = pick_vec(prob, {img, out});
+    msda::KernelArgs a;
+    fill_args(a, prob, vec);
+    a.img = img;
+    a.shapes = reinterpret_cast<const long long *>(img_shapes);
+    a.pts = sampling_points;
+    a.aw = attention_weights;
+    a.out = out;
+
+    cudaError_t e = cudaErrorNotSupported;
+    const bool tiled_ok = !force_generic() && vec * es == 16 && aligned(sampling_points, 16) &&
+                          aligned(attention_weights, 8);
+    if (tiled_ok) e = msda::launch_forward_tiled(a, prob->dtype, dev.sm_count, st);
+    if (e == cudaErrorNotSupported) e = msda::launch_forward_generic(a, prob->dtype, vec, dev.sm_count, st);
+    if (e != cudaSuccess) return fail_cuda(e, "msda_forward launch");
+    return MSDA_OK;
+}
+
+size_t msda_backward_workspace_bytes(const msda_problem *prob, int flags) {
+    if (validate(prob) != MSDA_OK) return 0;
+    size_t bytes = 0;
+    if ((flags & MSDA_BWD_NEED_IMG) && (prob->dtype == MSDA_DTYPE_F16 || prob->dtype == MSDA_DTYPE_BF16))
+        bytes += sizeof(float) * (size_t)prob->B * prob->Npix * prob->H * prob->D;
+    return bytes;
+}
+
+int msda_backward(void *grad_img, void *grad_points, void *grad_weights, const void *grad_out, const void *img,
+                  const int64_t *img_shapes, const void *sampling_points, const void *attention_weights,
+                  const msda_problem *prob, int flags, void *workspace, size_t workspace_bytes, void *stream) {
+    int rc = validate(prob);
+    if (rc != MSDA_OK) return rc;
+    if ((flags & MSDA_BWD_NEED_ALL) == 0) return MSDA_OK;
+    const bool need_img = flags & MSDA_BWD_NEED_IMG, need_pts = flags & MSDA_BWD_NEED_POINTS,
+               need_aw = flags & MSDA_BWD_NEED_WEIGHTS;
+    if ((need_img && !grad_img) || (need_pts && !grad_points) || (need_aw && !grad_weights))
+        return fail(MSDA_ERR_NULL_POINTER, "msda_backward: a requested gradient buffer is NULL");
+    const size_t es = dtype_size(prob->dtype);
+    const size_t img_elems = (size_t)prob->B * prob->Npix * prob->H * prob->D;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DeviceInfo dev;
+    rc = device_info(&dev);
+    if (rc != MSDA_OK) return rc;
+
+    // grad_img accumulates in fp32 (fp64 for f64): directly in grad_img for f32/f64, in the workspace for 16-bit.
+    const bool staged = need_img && (prob->dtype == MSDA_DTYPE_F16 || prob->dtype == MSDA_DTYPE_BF16);
+    void *accum = grad_img;
+    size_t accum_bytes = img_elems * es;
+    if (staged) {
+        const size_t want = msda_backward_workspace_bytes(prob, flags);
+        if (!workspace || workspace_bytes < want)
+            return fail(MSDA_ERR_WORKSPACE, "msda_backward: workspace of %zu bytes required, got %zu", want,
+                        workspace_bytes);
+        if (!aligned(workspace, 16)) return fail(MSDA_ERR_WORKSPACE, "msda_backward: workspace must be 16-byte aligned");
+        accum = workspace;
+        accum_bytes = img_elems * sizeof(float);
+    }
+    if (need_img && img_elems > 0) {
+        cudaError_t e = cudaMemsetAsync(accum, 0, accum_bytes, st);
+        if (e != cudaSuccess) return fail_cuda(e, "msda_backward zero-fill");
+    }
+    if (prob->B == 0 || prob->Q == 0) return MSDA_OK;
+    if (!grad_out || !img || !img_shapes || !sampling_points || !attention_weights)
+        return fail(MSDA_ERR_NULL_POINTER, "msda_backward: NULL device pointer");
+    if (!aligned(sampling_points, 2 * es) || !aligned(grad_points, 2 * es) || !aligned(img_shapes, 8))
+        return fail(MSDA_ERR_BAD_SHAPE, "msda_backward: sampling_points / grad_points must be aligned to one (x,y) pair");
+
+    // accumulation rows are CT-typed: alignment requirement scales with sizeof(CT)/sizeof(T)
+    const size_t acc_es = prob->dtype == MSDA_DTYPE_F64 ? 8 : 4;
+    int vec = pick_vec(prob, {img, grad_out});
+    while (vec > 1 && need_img && !aligned(accum, vec * acc_es > 16 ? 16 : vec * acc_es)) vec >>= 1;
+
+    msda::KernelArgs a;
+    fill_args(a, prob, vec);
+    a.img = img;
+    a.shapes = reinterpret_cast<const long long *>(img_shapes);
+    a.pts = sampling_points;
+    a.aw = attention_weights;
+    a.gout = grad_out;
+    a.gimg = accum;
+    a.gpts = grad_points;
+    a.gaw = grad_weights;
+    a.flags = flags & MSDA_BWD_NEED_ALL;
+
+    cudaError_t e = cudaErrorNotSupported;
+    const bool tiled_ok = !force_generic() && vec * es == 16 && aligned(sampling_points, 16) &&
+                          aligned(attention_weights, 8) && aligned(grad_points, 16) && aligned(grad_weights, 8) &&
+                          aligned(accum, 16);
+    if (tiled_ok) e = msda::launch_backward_tiled(a, prob->dtype, dev.sm_count, st);
+    if (e == cudaErrorNotSupported) e = msda::launch_backward_generic(a, prob->dtype, vec, dev.sm_count, st);
+    if (e != cudaSuccess) return fail_cuda(e, "msda_backward launch");
+
+    if (staged) {
+        e = msda::launch_round_grad_img(grad_img, static_cast<const float *>(accum), (long long)img_elems, prob->dtype, st);
+        if (e != cudaSuccess) return fail_cuda(e, "msda_backward grad_img rounding");
+    }
+    return MSDA_OK;
+}
+
+}  // extern "C"
+
+// -------------------------------------------------------------------------------------------------------------------
+// Level table as a stand-alone kernel + the L2 roof probes
+// -------------------------------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void level_table_kernel(int32_t *__restrict__ table, const long long *__restrict__ shapes, int L, int Npix) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        long long run = 0;
+        for (int l = 0; l < L; ++l) {
+            const long long h = shapes[2 * l], w = shapes[2 * l + 1];
+            table[4 * l + 0] = (int32_t)h;
+            table[4 * l + 1] = (int32_t)w;
+            table[4 * l + 2] = (int32_t)run;
+            table[4 * l + 3] = 0;
+            run += h * w;
+        }
+        table[4 * L + 0] = (int32_t)run;
+        table[4 * L + 1] = Npix;
+        table[4 * L + 2] = run == (long long)Npix;
+        table[4 * L + 3] = 0;
+    }
+}
+
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16;
+    x *= 0x7feb352dU;
+    x ^= x >> 15;
+    x *= 0x846ca68bU;
+    x ^= x >> 16;
+    return x;
+}
+
+// One 8-lane group per 128-byte row, 8 independent rows in flight per lane: the access shape of the MSDA gathers.
+__global__ void __launch_bounds__(512) probe_gather_kernel(float *__restrict__ sink, const float *__restrict__ buf,
+                                                           long long buf_rows, long long rows, uint32_t seed) {
+    const int j = threadIdx.x & 7;
+    const long long group = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const long long ngroups = ((long long)gridDim.x * blockDim.x) >> 3;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long r = group * 8; r < rows; r += ngroups * 8) {
+        float4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t hsh = mix32((uint32_t)(r + i) * 2654435761U + seed);
+            const long long row = (long long)(((unsigned long long)hsh * (unsigned long long)buf_rows) >> 32);
+            v[i] = __ldg(reinterpret_cast<const float4 *>(buf + row * 32 + j * 4));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            acc.x += v[i].x;
+            acc.y += v[i].y;
+            acc.z += v[i].z;
+            acc.w += v[i].w;
+        }
+    }
+    if (acc.x + acc.y + acc.z + acc.w == 123456.789f) sink[0] = acc.x;  // keeps the loads alive
+}
+
+__global__ void __launch_bounds__(512) probe_scatter_kernel(float *__restrict__ buf, long long buf_rows, long long rows,
+                                                            uint32_t seed) {
+    const int j = threadIdx.x & 7;
+    const long long group = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const long long ngroups = ((long long)gridDim.x * blockDim.x) >> 3;
+    for (long long r = group * 8; r < rows; r += ngroups * 8) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t hsh = mix32((uint32_t)(r + i) * 2654435761U + seed);
+            const long long row = (long long)(((unsigned long long)hsh * (unsigned long long)buf_rows) >> 32);
+            msda::red_add_v4(buf + row * 32 + j * 4, 1.0f, 1.0f, 1.0f, 1.0f);
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int msda_level_table(int32_t *table, const int64_t *img_shapes, int64_t L, int64_t Npix, void *stream) {
+    if (!table || !img_shapes) return fail(MSDA_ERR_NULL_POINTER, "msda_level_table: NULL device pointer");
+    if (L <= 0 || L > 2048 || Npix < 0 || Npix > 0x7fffffffLL) return fail(MSDA_ERR_BAD_SHAPE, "msda_level_table: bad L / Npix");
+    level_table_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        table, reinterpret_cast<const long long *>(img_shapes), (int)L, (int)Npix);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(e, "msda_level_table launch");
+    return MSDA_OK;
+}
+
+int msda_probe_gather(float *sink, const float *buf, int64_t buf_rows, int64_t rows, uint32_t seed, void *stream) {
+    if (!sink || !buf || buf_rows <= 0 || rows <= 0) return fail(MSDA_ERR_BAD_SHAPE, "msda_probe_gather: bad arguments");
+    DeviceInfo dev;
+    int rc = device_info(&dev);
+    if (rc != MSDA_OK) return rc;
+    probe_gather_kernel<<<dev.sm_count * 2, 512, 0, static_cast<cudaStream_t>(stream)>>>(sink, buf, buf_rows, rows, seed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(e, "msda_probe_gather launch");
+    return MSDA_OK;
+}
+
+int msda_probe_scatter(float *buf, int64_t buf_rows, int64_t rows, uint32_t seed, void *stream) {
+    if (!buf || buf_rows <= 0 || rows <= 0) return fail(MSDA_ERR_BAD_SHAPE, "msda_probe_scatter: bad arguments");
+    DeviceInfo dev;
+    int rc = device_info(&dev);
+    if (rc != MSDA_OK) return rc;
+    probe_scatter_kernel<<<dev.sm_count * 2, 512, 0, static_cast<cudaStream_t>(stream)>>>(buf, buf_rows, rows, seed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(e, "msda_probe_scatter launch");
+    return MSDA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,442 @@
+// msda_bwd.cu -- backward kernels: one pass that recomputes the forward sampling and produces
+//   grad_attention_weights[p] = sum_d go[d] * sample_p[d]                                   (kernels.py:494)
+//   grad_sampling_points[p]   = sum_d go[d] * w_p * scale * d(sample_p[d])/d(x|y)           (kernels.py:510-524)
+//   grad_img[corner rows]    += go * w_p * bilinear_weight                                  (kernels.py:543-553)
+// Replaces the reference's Triton backward (src/msda_triton/kernels.py:396-553, launched from :556-592).
+//
+// grad_img is scattered with relaxed, result-less vector reductions (red.global.add.v4.f32 -> REDG.E.ADD.F32x4),
+// always into an fp32 (fp64 for fp64 storage) accumulation image, so 16-bit storage does not lose the small
+// contributions the reference's fp16 atomics drop.  The gradient w.r.t. a sampling point is w.r.t. the NORMALISED
+// [0,1] coordinate, hence the (w-1)|w scale factor.
+#include "msda_common.cuh"
+#include "msda_launch.h"
+#include "msda_tiled.cuh"
+
+namespace msda {
+
+constexpr int kNeedImg = 1, kNeedPts = 2, kNeedAw = 4;
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) msda_bwd_generic_kernel(const KernelArgs a) {
+    using CT = typename Traits<T>::CT;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    Level *s_lv = reinterpret_cast<Level *>(s_raw);
+    build_level_table(s_lv, a.shapes, a.L);
+
+    const T *__restrict__ img = static_cast<const T *>(a.img);
+    const T *__restrict__ pts = static_cast<const T *>(a.pts);
+    const T *__restrict__ aw = static_cast<const T *>(a.aw);
+    const T *__restrict__ gout = static_cast<const T *>(a.gout);
+    CT *__restrict__ gimg = static_cast<CT *>(a.gimg);
+    T *__restrict__ gpts = static_cast<T *>(a.gpts);
+    T *__restrict__ gaw = static_cast<T *>(a.gaw);
+
+    const int lanes = a.lanes;
+    const int j = threadIdx.x & (lanes - 1);
+    const int group = threadIdx.x / lanes;
+    const int groups_per_cta = blockDim.x / lanes;
+    const bool border = a.border != 0, align = a.align != 0;
+    const bool need_img = (a.flags & kNeedImg) != 0, need_pts = (a.flags & kNeedPts) != 0,
+               need_aw = (a.flags & kNeedAw) != 0;
+    const size_t row_stride = (size_t)a.H * a.D;
+    const int LK = a.LK;
+
+    for (long long ubase = (long long)blockIdx.x * groups_per_cta; ubase < a.units;
+         ubase += (long long)gridDim.x * groups_per_cta) {
+        const long long u_raw = ubase + group;
+        const bool live = u_raw < a.units;
+        const long long u = live ? u_raw : a.units - 1;
+        const int h = (int)(u % a.H);
+        const long long b = u / ((long long)a.H * a.Q);
+        const size_t bh_off = ((size_t)b * a.Npix * a.H + h) * a.D;
+        const T *__restrict__ img_bh = img + bh_off;
+        CT *__restrict__ gimg_bh = gimg + bh_off;
+        const T *__restrict__ pts_u = pts + (size_t)u * LK * 2;
+        const T *__restrict__ aw_u = aw + (size_t)u * LK;
+        const T *__restrict__ go_u = gout + (size_t)u * a.D;
+        const bool scatter = need_img && live;  // dead groups shadow the last unit and must not add twice
+
+        // grad_out slice of chunk 0 stays in registers for the whole unit
+        CT go0[VEC];
+        {
+            const int c0 = j * VEC;
+            if (c0 < a.D) {
+                load_vec<T, VEC>(go_u + c0, go0);
+            } else {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) go0[e] = (CT)0;
+            }
+        }
+
+        for (int base = 0; base < LK; base += lanes) {
+            Tap<CT> t;
+            t.row00 = 0;
+            t.pack = 0;
+            t.dx = t.dy = (CT)0;
+            CT w_att = (CT)0, sx = (CT)0, sy = (CT)0;
+            const int p = base + j;
+            if (p < LK) {
+                const Level lv = s_lv[p / a.K];
+                CT xy[2];
+                load_vec<T, 2>(pts_u + 2 * p, xy);
+                w_att = Traits<T>::to_ct(aw_u[p]);
+                t = locate<CT>(xy[0], xy[1], lv, border, align);
+                sx = align ? (CT)(lv.w - 1) : (CT)lv.w;
+                sy = align ? (CT)(lv.h - 1) : (CT)lv.h;
+            }
+            CT my_gw = (CT)0, my_gx = (CT)0, my_gy = (CT)0;
+
+            const int n = min(lanes, LK - base);
+            for (int i = 0; i < n; ++i) {
+                const int row00 = __shfl_sync(0xffffffffu, t.row00, i, lanes);
+                const int pack = __shfl_sync(0xffffffffu, t.pack, i, lanes);
+                const CT dx = shfl_ct(t.dx, i, lanes);
+                const CT dy = shfl_ct(t.dy, i, lanes);
+                const CT wa = shfl_ct(w_att, i, lanes);
+                const int step_y = pack & kPackDyMask;
+                const int step_x = (pack >> kPackDxBit) & 1;
+                const unsigned mask = (unsigned)(pack >> kPackMaskShift) & 0xFu;
+                const CT b00 = ((CT)1 - dy) * ((CT)1 - dx), b01 = ((CT)1 - dy) * dx;
+                const CT b10 = dy * ((CT)1 - dx), b11 = dy * dx;
+                const size_t r00 = (size_t)row00 * row_stride;
+                const size_t r01 = r00 + (size_t)step_x * row_stride;
+                const size_t r10 = r00 + (size_t)step_y * row_stride;
+                const size_t r11 = r10 + (size_t)step_x * row_stride;
+
+                CT d00 = (CT)0, d01 = (CT)0, d10 = (CT)0, d11 = (CT)0;  // per-corner <go, v> over my channels
+                for (int chunk = 0; chunk < a.chunks; ++chunk) {
+                    const int c0 = (chunk * lanes + j) * VEC;
+                    if (c0 >= a.D) continue;
+                    CT go[VEC];
+                    if (chunk == 0) {
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) go[e] = go0[e];
+                    } else {
+                        load_vec<T, VEC>(go_u + c0, go);
+                    }
+                    CT v[VEC], g[VEC];
+                    if (mask & 1u) {
+                        load_vec<T, VEC>(img_bh + r00 + c0, v);
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) d00 += go[e] * v[e];
+                        if (scatter) {
+                            const CT s = wa * b00;
+#pragma unroll
+                            for (int e = 0; e < VEC; ++e) g[e] = go[e] * s;
+                            red_add_vec<VEC>(gimg_bh + r00 + c0, g);
+                        }
+                    }
+                    if (mask & 2u) {
+                        load_vec<T, VEC>(img_bh + r01 + c0, v);
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) d01 += go[e] * v[e];
+                        if (scatter) {
+                            const CT s = wa * b01;
+#pragma unroll
+                            for (int e = 0; e < VEC; ++e) g[e] = go[e] * s;
+                            red_add_vec<VEC>(gimg_bh + r01 + c0, g);
+                        }
+                    }
+                    if (mask & 4u) {
+                        load_vec<T, VEC>(img_bh + r10 + c0, v);
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) d10 += go[e] * v[e];
+                        if (scatter) {
+                            const CT s = wa * b10;
+#pragma unroll
+                            for (int e = 0; e < VEC; ++e) g[e] = go[e] * s;
+                            red_add_vec<VEC>(gimg_bh + r10 + c0, g);
+                        }
+                    }
+                    if (mask & 8u) {
+                        load_vec<T, VEC>(img_bh + r11 + c0, v);
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) d11 += go[e] * v[e];
+                        if (scatter) {
+                            const CT s = wa * b11;
+#pragma unroll
+                            for (int e = 0; e < VEC; ++e) g[e] = go[e] * s;
+                            red_add_vec<VEC>(gimg_bh + r11 + c0, g);
+                        }
+                    }
+                }
+                // masked corners contribute value 0 (kernels.py:227-231), which is what d?? == 0 encodes
+                CT s_w = b00 * d00 + b01 * d01 + b10 * d10 + b11 * d11;
+                CT s_x = ((CT)1 - dy) * (d01 - d00) + dy * (d11 - d10);
+                CT s_y = ((CT)1 - dx) * (d10 - d00) + dx * (d11 - d01);
+                for (int m = lanes >> 1; m > 0; m >>= 1) {
+                    s_w += shfl_xor_ct(s_w, m);
+                    s_x += shfl_xor_ct(s_x, m);
+                    s_y += shfl_xor_ct(s_y, m);
+                }
+                if (j == i) {
+                    my_gw = s_w;
+                    my_gx = s_x;
+                    my_gy = s_y;
+                }
+            }
+            if (live && p < LK) {
+                if (need_aw) gaw[(size_t)u * LK + p] = Traits<T>::from_ct(my_gw);
+                if (need_pts) {
+                    CT g2[2] = {my_gx * (w_att * sx), my_gy * (w_att * sy)};
+                    store_vec<T, 2>(gpts + ((size_t)u * LK + p) * 2, g2);
+                }
+            }
+        }
+    }
+}
+
+template <typename T, int VEC> static cudaError_t launch_generic(const KernelArgs &a, int sm_count, cudaStream_t st) {
+    const int threads = 256;
+    const int groups_per_cta = threads / a.lanes;
+    long long want = (a.units + groups_per_cta - 1) / groups_per_cta;
+    const long long cap = (long long)sm_count * 16;
+    const int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+    const size_t smem = sizeof(Level) * (size_t)a.L;
+    msda_bwd_generic_kernel<T, VEC><<<grid, threads, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <typename T> static cudaError_t dispatch_vec(const KernelArgs &a, int vec, int sm_count, cudaStream_t st) {
+    switch (vec) {
+        case 8:
+            if constexpr (Traits<T>::kMaxVec >= 8) return launch_generic<T, 8>(a, sm_count, st);
+            break;
+        case 4:
+            if constexpr (Traits<T>::kMaxVec >= 4) return launch_generic<T, 4>(a, sm_count, st);
+            break;
+        case 2:
+            return launch_generic<T, 2>(a, sm_count, st);
+        case 1:
+            return launch_generic<T, 1>(a, sm_count, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_backward_generic(const KernelArgs &a, int dtype, int vec, int sm_count, cudaStream_t st) {
+    switch (dtype) {
+        case 0: return dispatch_vec<float>(a, vec, sm_count, st);
+        case 1: return dispatch_vec<__half>(a, vec, sm_count, st);
+        case 2: return dispatch_vec<__nv_bfloat16>(a, vec, sm_count, st);
+        case 3: return dispatch_vec<double>(a, vec, sm_count, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Tuned backward: same persistent (b,h)-major schedule and lane layout as the tuned forward.
+//
+// Per sampling point every lane forms, over its VEC channels, the four corner dot products <go, v_c>; from them the
+// three per-point partials (grad weight, d/dx, d/dy).  The 3*LK partials of a unit live in registers until the
+// end of the unit and are then reduced across the LANES lanes with a TRANSPOSING butterfly (each step halves the
+// values a lane keeps), which costs 3*LK*(1 - 1/LANES) shuffles instead of 3*LK*log2(LANES) and leaves lane j
+// holding exactly the PPL points it loaded -- so the grad_points / grad_weights stores are the same coalesced
+// vector stores as the loads.  grad_img goes out as one REDG.E.ADD.F32x4 per lane per valid corner.
+// ---------------------------------------------------------------------------------------------------------------
+template <int N, int STEP> __device__ __forceinline__ void transpose_reduce(float (&part)[N], const int j) {
+    // lanes with bit STEP clear keep the lower half, their partners (j ^ STEP) the upper half
+    constexpr int HALF = N / 2;
+    const bool upper = (j & STEP) != 0;
+#pragma unroll
+    for (int k = 0; k < HALF; ++k) {
+        const float keep = upper ? part[k + HALF] : part[k];
+        const float send = upper ? part[k] : part[k + HALF];
+        part[k] = keep + __shfl_xor_sync(0xffffffffu, send, STEP);
+    }
+    if constexpr (STEP > 1) {
+        float(&lower)[HALF] = reinterpret_cast<float(&)[HALF]>(part);
+        transpose_reduce<HALF, STEP / 2>(lower, j);
+    }
+}
+
+template <typename T, int LANES, int LK, bool BORDER>
+__global__ void __launch_bounds__(kTiledThreads, 1)
+    msda_bwd_tiled_kernel(const KernelArgs a, const int tiles_per_bh, const long long total_tiles) {
+    using Cfg = TiledCfg<T, LANES, LK>;
+    constexpr int VEC = Cfg::VEC, G = Cfg::G, PPL = Cfg::PPL;
+    constexpr int NB = 2;  // points per gather batch (8 gathers in flight per lane; registers also hold 3*LK partials)
+    static_assert(LANES % NB == 0, "batch must divide the group");
+
+    __shared__ Level s_lv[LK];
+    build_level_table(s_lv, a.shapes, a.L);
+
+    const T *__restrict__ img = static_cast<const T *>(a.img);
+    const T *__restrict__ pts = static_cast<const T *>(a.pts);
+    const T *__restrict__ aw = static_cast<const T *>(a.aw);
+    const T *__restrict__ gout = static_cast<const T *>(a.gout);
+    float *__restrict__ gimg = static_cast<float *>(a.gimg);
+    T *__restrict__ gpts = static_cast<T *>(a.gpts);
+    T *__restrict__ gaw = static_cast<T *>(a.gaw);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int j = lane % LANES, g = lane / LANES;
+    const bool align = a.align != 0;
+    const bool need_img = (a.flags & kNeedImg) != 0, need_pts = (a.flags & kNeedPts) != 0,
+               need_aw = (a.flags & kNeedAw) != 0;
+    const size_t row_stride = (size_t)a.H * a.D;
+
+    const long long t_begin = total_tiles * blockIdx.x / gridDim.x;
+    const long long t_end = total_tiles * (blockIdx.x + 1) / gridDim.x;
+
+    for (long long tile = t_begin + warp; tile < t_end; tile += nwarps) {
+        const TileUnit tu = decode_tile(tile, tiles_per_bh, g, G, a);
+        const T *__restrict__ img_lane = img + tu.bh_off + j * VEC;
+        float *__restrict__ gimg_lane = gimg + tu.bh_off + j * VEC;
+        const bool scatter = need_img && tu.live;
+
+        float xy[2 * PPL], wa[PPL], sx[PPL], sy[PPL];
+        load_vec<T, 2 * PPL>(pts + ((size_t)tu.u * LK + j * PPL) * 2, xy);
+        load_vec<T, PPL>(aw + (size_t)tu.u * LK + j * PPL, wa);
+        Tap<float> tap[PPL];
+#pragma unroll
+        for (int pp = 0; pp < PPL; ++pp) {
+            const Level lv = s_lv[(j * PPL + pp) / a.K];
+            tap[pp] = locate<float>(xy[2 * pp], xy[2 * pp + 1], lv, BORDER, align);
+            sx[pp] = align ? (float)(lv.w - 1) : (float)lv.w;
+            sy[pp] = align ? (float)(lv.h - 1) : (float)lv.h;
+        }
+        float go[VEC];
+        load_vec<T, VEC>(gout + (size_t)tu.u * a.D + j * VEC, go);
+
+        // part[(jj*PPL + pp)*3 + {0,1,2}] : point jj*PPL+pp  ->  {grad weight, d/dx, d/dy} partial over my channels
+        float part[3 * LK];
+
+#pragma unroll
+        for (int pp = 0; pp < PPL; ++pp) {
+#pragma unroll
+            for (int jj0 = 0; jj0 < LANES; jj0 += NB) {
+                uint4 raw[NB][4];
+                float fx[NB], fy[NB], fw[NB];
+                size_t off[NB][4];
+                unsigned msk[NB];
+#pragma unroll
+                for (int n = 0; n < NB; ++n) {
+                    const int src = jj0 + n;
+                    const int row00 = __shfl_sync(0xffffffffu, tap[pp].row00, src, LANES);
+                    const int pack = __shfl_sync(0xffffffffu, tap[pp].pack, src, LANES);
+                    fx[n] = __shfl_sync(0xffffffffu, tap[pp].dx, src, LANES);
+                    fy[n] = __shfl_sync(0xffffffffu, tap[pp].dy, src, LANES);
+                    fw[n] = __shfl_sync(0xffffffffu, wa[pp], src, LANES);
+                    const int step_y = pack & kPackDyMask;
+                    const int step_x = (pack >> kPackDxBit) & 1;
+                    msk[n] = BORDER ? 0xFu : ((unsigned)(pack >> kPackMaskShift) & 0xFu);
+                    off[n][0] = (size_t)row00 * row_stride;
+                    off[n][1] = off[n][0] + (size_t)step_x * row_stride;
+                    off[n][2] = off[n][0] + (size_t)step_y * row_stride;
+                    off[n][3] = off[n][2] + (size_t)step_x * row_stride;
+                    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        raw[n][c] = (BORDER || ((msk[n] >> c) & 1u)) ? gather_row<T>(img_lane + off[n][c]) : zero;
+                }
+#pragma unroll
+                for (int n = 0; n < NB; ++n) {
+                    const float dx = fx[n], dy = fy[n];
+                    float bw[4];  // bilinear weights of corners 00, 01, 10, 11
+                    bw[1] = (1.0f - dy) * dx;
+                    bw[0] = (1.0f - dy) - bw[1];
+                    bw[3] = dy * dx;
+                    bw[2] = dy - bw[3];
+                    float d[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        float v[VEC];
+                        widen_row<T, VEC>(raw[n][c], v);
+                        float acc = 0.0f;
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) acc = fmaf(go[e], v[e], acc);
+                        d[c] = acc;
+                        if (scatter && (BORDER || ((msk[n] >> c) & 1u))) {
+                            const float s = fw[n] * bw[c];
+                            float gv[VEC];
+#pragma unroll
+                            for (int e = 0; e < VEC; ++e) gv[e] = go[e] * s;
+                            red_add_vec<VEC>(gimg_lane + off[n][c], gv);
+                        }
+                    }
+                    const int pidx = (jj0 + n) * PPL + pp;
+                    part[3 * pidx + 0] = bw[0] * d[0] + bw[1] * d[1] + bw[2] * d[2] + bw[3] * d[3];
+                    part[3 * pidx + 1] = (1.0f - dy) * (d[1] - d[0]) + dy * (d[3] - d[2]);
+                    part[3 * pidx + 2] = (1.0f - dx) * (d[2] - d[0]) + dx * (d[3] - d[1]);
+                }
+            }
+        }
+
+        // ---- reduce over the LANES lanes; lane j ends with points [j*PPL, (j+1)*PPL) in part[0 .. 3*PPL) ----
+        transpose_reduce<3 * LK, LANES / 2>(part, j);
+
+        if (tu.live) {
+            if (need_aw) {
+                float gw[PPL];
+#pragma unroll
+                for (int pp = 0; pp < PPL; ++pp) gw[pp] = part[3 * pp + 0];
+                store_vec<T, PPL>(gaw + (size_t)tu.u * LK + j * PPL, gw);
+            }
+            if (need_pts) {
+                float gp[2 * PPL];
+#pragma unroll
+                for (int pp = 0; pp < PPL; ++pp) {
+                    gp[2 * pp + 0] = part[3 * pp + 1] * (wa[pp] * sx[pp]);
+                    gp[2 * pp + 1] = part[3 * pp + 2] * (wa[pp] * sy[pp]);
+                }
+                store_vec<T, 2 * PPL>(gpts + ((size_t)tu.u * LK + j * PPL) * 2, gp);
+            }
+        }
+    }
+}
+
+template <typename T, int LANES, int LK>
+static cudaError_t launch_tiled_t(const KernelArgs &a, int sm_count, cudaStream_t st) {
+    constexpr int G = TiledCfg<T, LANES, LK>::G;
+    const int tiles_per_bh = (a.Q + G - 1) / G;
+    const long long total_tiles = (long long)a.B * a.H * tiles_per_bh;
+    const int warps = kTiledThreads / 32;
+    long long want = (total_tiles + warps - 1) / warps;
+    const int grid = (int)(want < sm_count ? (want < 1 ? 1 : want) : sm_count);
+    if (a.border)
+        msda_bwd_tiled_kernel<T, LANES, LK, true><<<grid, kTiledThreads, 0, st>>>(a, tiles_per_bh, total_tiles);
+    else
+        msda_bwd_tiled_kernel<T, LANES, LK, false><<<grid, kTiledThreads, 0, st>>>(a, tiles_per_bh, total_tiles);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_backward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st) {
+    if (a.LK != 16 || a.L > 16) return cudaErrorNotSupported;
+    if (dtype == 0) {
+        if (a.D == 32) return launch_tiled_t<float, 8, 16>(a, sm_count, st);
+        if (a.D == 64) return launch_tiled_t<float, 16, 16>(a, sm_count, st);
+    } else if (dtype == 1) {
+        if (a.D == 32) return launch_tiled_t<__half, 4, 16>(a, sm_count, st);
+        if (a.D == 64) return launch_tiled_t<__half, 8, 16>(a, sm_count, st);
+    } else if (dtype == 2) {
+        if (a.D == 32) return launch_tiled_t<__nv_bfloat16, 4, 16>(a, sm_count, st);
+        if (a.D == 64) return launch_tiled_t<__nv_bfloat16, 8, 16>(a, sm_count, st);
+    }
+    return cudaErrorNotSupported;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 16-bit storage epilogue: grad_img[T] = round(accumulation image[fp32]).
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T> __global__ void round_grad_img_kernel(T *__restrict__ dst, const float *__restrict__ src, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        dst[i] = Traits<T>::from_ct(src[i]);
+}
+
+cudaError_t launch_round_grad_img(void *dst, const float *src, long long n, int dtype, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    const int threads = 256;
+    long long want = (n + threads - 1) / threads;
+    const int grid = (int)(want > 148 * 32 ? 148 * 32 : want);
+    if (dtype == 1)
+        round_grad_img_kernel<__half><<<grid, threads, 0, st>>>(static_cast<__half *>(dst), src, n);
+    else if (dtype == 2)
+        round_grad_img_kernel<__nv_bfloat16><<<grid, threads, 0, st>>>(static_cast<__nv_bfloat16 *>(dst), src, n);
+    else
+        return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
+}  // namespace msda

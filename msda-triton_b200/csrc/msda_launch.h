@@ -1,0 +1,21 @@
+// msda_launch.h -- internal launcher declarations (not part of the C ABI; see include/msda_b200.h for that).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "msda_common.cuh"
+
+namespace msda {
+
+// dtype codes follow enum msda_dtype: 0 f32, 1 f16, 2 bf16, 3 f64.
+cudaError_t launch_forward_generic(const KernelArgs &a, int dtype, int vec, int sm_count, cudaStream_t st);
+cudaError_t launch_backward_generic(const KernelArgs &a, int dtype, int vec, int sm_count, cudaStream_t st);
+
+// Tuned paths (D*sizeof(T) == 128 or 64 bytes per row, L*K == 16).  Return cudaErrorNotSupported when the problem
+// does not fit so the caller falls through to the generic kernels.
+cudaError_t launch_forward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st);
+cudaError_t launch_backward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st);
+
+// grad_img epilogue for 16-bit storage: rounds the fp32 accumulation image to T.
+cudaError_t launch_round_grad_img(void *dst, const float *src, long long n, int dtype, cudaStream_t st);
+
+}  // namespace msda

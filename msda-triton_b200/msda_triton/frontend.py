@@ -1,0 +1,254 @@
+"""Public surface of the package: same names, signatures, layouts and state_dict keys as rziga/msda-triton
+(``/root/reference/src/msda_triton/frontend.py``), with the CUDA route backed by libmsda_b200.so.
+
+Name map (reference line -> here):
+  multiscale_deformable_attention          frontend.py:145-172 -> multiscale_deformable_attention (device dispatch)
+  triton_multiscale_deformable_attention   frontend.py:71-105  -> b200_multiscale_deformable_attention (+ alias)
+  _TritonMultiscaleDeformableAttentionFunction  frontend.py:108-142 -> _B200MsdaFunction
+  native_multiscale_deformable_attention   frontend.py:15-68   -> native_multiscale_deformable_attention (CPU tensors)
+  MultiscaleDeformableAttention            frontend.py:175-292 -> MultiscaleDeformableAttention
+
+Dispatch rule.  The reference tries its GPU kernel and silently re-runs ANY failure on the slow torch route
+(``except Exception``, frontend.py:170).  Here the route is chosen by the device of ``img`` and nothing is caught:
+CUDA tensors always run the hand-written sm_100a kernels (errors propagate; a missing library raises), CPU tensors
+run the torch route the reference documents for ``device="cpu"`` (README.md:132).
+"""
+from __future__ import annotations
+
+from typing import Literal
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+from torch.amp import custom_bwd, custom_fwd
+from torch.autograd.function import once_differentiable
+
+from . import kernels
+
+PaddingMode = Literal["border", "zeros"]
+
+# dtypes of the CUDA route: the reference's three (frontend.py:84) plus bf16, which its Triton helper rejects
+# (kernels.py:40-41) and therefore sends down the torch route.
+CUDA_DTYPES = (torch.float16, torch.bfloat16, torch.float32, torch.float64)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU-tensor route
+# ---------------------------------------------------------------------------------------------------------------------
+def native_multiscale_deformable_attention(
+    img: torch.Tensor,
+    img_shapes: torch.Tensor,
+    sampling_points: torch.Tensor,
+    attention_weights: torch.Tensor,
+    padding_mode: PaddingMode,
+    align_corners: bool,
+) -> torch.Tensor:
+    """Torch-operator route (``F.grid_sample`` per level), differentiable through autograd.
+
+    Serves CPU tensors.  It is never entered for CUDA inputs by :func:`multiscale_deformable_attention`; calling it
+    directly with CUDA tensors works (the reference's tests and benchmark do, as the "torch" comparison line).
+    """
+    batch, _, heads, channels = img.shape
+    queries, points = sampling_points.shape[1], sampling_points.shape[4]
+    level_hw = [(int(h), int(w)) for h, w in img_shapes.tolist()]
+    grids = sampling_points.mul(2).sub(1)                     # grid_sample wants [-1, 1]
+    per_level = img.split([h * w for h, w in level_hw], dim=1)
+    sampled = []
+    for lvl, (h, w) in enumerate(level_hw):
+        # [B, h*w, H, C] -> [B*H, C, h, w]
+        feat = per_level[lvl].permute(0, 2, 3, 1).reshape(batch * heads, channels, h, w)
+        # [B, N, H, P, 2] -> [B*H, N, P, 2]
+        grid = grids[:, :, :, lvl].permute(0, 2, 1, 3, 4).reshape(batch * heads, queries, points, 2)
+        val = F.grid_sample(feat, grid, mode="bilinear", padding_mode=padding_mode, align_corners=align_corners)
+        # [B*H, C, N, P] -> [B, N, H, P, C]
+        sampled.append(val.reshape(batch, heads, channels, queries, points).permute(0, 3, 1, 4, 2))
+    sampled = torch.stack(sampled, dim=3)                     # [B, N, H, L, P, C]
+    return (attention_weights.unsqueeze(-1) * sampled).sum(dim=(3, 4))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CUDA route
+# ---------------------------------------------------------------------------------------------------------------------
+class _B200MsdaFunction(torch.autograd.Function):
+    """Autograd boundary.  Contract identical to the reference's Function (frontend.py:108-142): under autocast the
+    float inputs are cast to fp32 and the op runs in fp32; the four input tensors are saved (no intermediates, so
+    extra memory = outputs only); backward is once-differentiable and returns grads for (img, None, points, weights,
+    None, None).  Additionally ``ctx.needs_input_grad`` is honoured so unneeded gradients are not computed."""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, img, img_shapes, sampling_points, attention_weights, padding_mode, align_corners):
+        ctx.save_for_backward(img, img_shapes, sampling_points, attention_weights)
+        ctx.padding_mode = padding_mode
+        ctx.align_corners = align_corners
+        return kernels.b200_multi_scale_deformable_attention_fwd(
+            img, img_shapes, sampling_points, attention_weights, padding_mode, align_corners)
+
+    @staticmethod
+    @once_differentiable
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, out_grad):
+        img, img_shapes, sampling_points, attention_weights = ctx.saved_tensors
+        needs = (ctx.needs_input_grad[0], ctx.needs_input_grad[2], ctx.needs_input_grad[3])
+        img_grad, points_grad, weights_grad = kernels.b200_multi_scale_deformable_attention_bwd(
+            out_grad, img, img_shapes, sampling_points, attention_weights, ctx.padding_mode, ctx.align_corners,
+            needs=needs)
+        return img_grad, None, points_grad, weights_grad, None, None
+
+
+def b200_multiscale_deformable_attention(
+    img: torch.Tensor,
+    img_shapes: torch.Tensor,
+    sampling_points: torch.Tensor,
+    attention_weights: torch.Tensor,
+    padding_mode: PaddingMode,
+    align_corners: bool,
+) -> torch.Tensor:
+    """CUDA route: validation (same two ``ValueError`` classes as frontend.py:84-95) then the autograd Function."""
+    for name, tensor in (("img", img), ("sampling_points", sampling_points), ("attention_weights", attention_weights)):
+        if tensor.dtype not in CUDA_DTYPES:
+            raise ValueError(f"Dtype of `{name}` should be in {list(CUDA_DTYPES)}, but got {tensor.dtype}.")
+    devices = [t.device for t in (img, img_shapes, sampling_points, attention_weights)]
+    if any(d.type != "cuda" for d in devices):
+        raise ValueError(f"Expected all inputs to be on gpu, but got {devices}.")
+    if len({d.index for d in devices}) != 1:
+        raise ValueError(f"Expected all inputs to be on the same gpu, but got {devices}.")
+    if padding_mode not in ("border", "zeros"):
+        raise ValueError(f"`padding_mode` should be 'border' or 'zeros', but got {padding_mode!r}.")
+    if not torch.is_autocast_enabled("cuda"):
+        # the kernels take one storage dtype; mixed inputs are promoted (under autocast custom_fwd casts to fp32)
+        common = torch.promote_types(torch.promote_types(img.dtype, sampling_points.dtype), attention_weights.dtype)
+        img, sampling_points, attention_weights = (t.to(common) for t in (img, sampling_points, attention_weights))
+    return _B200MsdaFunction.apply(img, img_shapes, sampling_points, attention_weights, padding_mode, bool(align_corners))
+
+
+# The reference's tests and benchmark import the CUDA route under this name (tests/test_msda.py:8-12).
+triton_multiscale_deformable_attention = b200_multiscale_deformable_attention
+
+
+def multiscale_deformable_attention(
+    img: torch.Tensor,
+    img_shapes: torch.Tensor,
+    sampling_points: torch.Tensor,
+    attention_weights: torch.Tensor,
+    padding_mode: PaddingMode,
+    align_corners: bool,
+) -> torch.Tensor:
+    """
+    Differentiable multiscale deformable attention function.
+
+    Args:
+        img (torch.Tensor): Flattened image pyramid tensor of shape `[batch_size, num_image, num_head, num_channel]`,
+            where `num_image=sum(h[i]*w[i] for i in range(levels))`.
+        img_shapes (torch.Tensor): Shapes of each pyramid level, tensor of shape `[num_levels, 2]`, (height, width) order.
+        sampling_points (torch.Tensor): Tensor of shape `[batch_size, num_queries, num_heads, num_levels, num_points, 2]`,
+            (x, y) order, normalized to [0, 1] with (0, 0) the top-left and (1, 1) the bottom-right corner.
+        attention_weights (torch.Tensor): Tensor of shape `[batch_size, num_queries, num_heads, num_levels, num_points]`.
+        padding_mode (Literal["border", "zeros"]): Out-of-bounds samples take the closest pixel (`border`) or 0 (`zeros`).
+        align_corners (bool): Grid alignment, as in `torch.nn.functional.grid_sample`.
+
+    Returns:
+        output (torch.Tensor): Output tensor of shape `[batch_size, num_queries, num_heads, num_channels]`.
+    """
+    if img.device.type == "cuda":
+        if img_shapes.device != img.device:
+            img_shapes = img_shapes.to(img.device, non_blocking=True)   # 16*L bytes; the kernels read it on device
+        return b200_multiscale_deformable_attention(
+            img, img_shapes, sampling_points, attention_weights, padding_mode, align_corners)
+    return native_multiscale_deformable_attention(
+        img, img_shapes, sampling_points, attention_weights, padding_mode, align_corners)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Module
+# ---------------------------------------------------------------------------------------------------------------------
+class MultiscaleDeformableAttention(nn.Module):
+    """
+    Multiscale deformable attention module (Deformable DETR, https://arxiv.org/abs/2010.04159, Figure 2): input and
+    output projections around :func:`multiscale_deformable_attention`.
+
+    Constructor signature, attribute names and parameter names (``img_input_proj``, ``query_input_proj``,
+    ``query_output_proj``) match the reference module (frontend.py:199-223) so checkpoints load unchanged.
+
+    Args:
+        emb_dim (int): Feature dimension of inputs.
+        hidden_dim (int): Feature dimension to which to project. Must be divisible by `num_heads`.
+        num_levels (int): Number of feature levels of input images.
+        num_heads (int): Number of attention heads.
+        num_points (int): Number of sampling points per level.
+        padding_mode (Literal["border", "zeros"]): See :func:`multiscale_deformable_attention`.
+        align_corners (bool): See :func:`multiscale_deformable_attention`.
+
+    Raises:
+        ValueError: If `hidden_dim` is not divisible by `num_heads`.
+    """
+
+    def __init__(
+        self,
+        emb_dim: int,
+        hidden_dim: int,
+        num_levels: int,
+        num_heads: int,
+        num_points: int,
+        padding_mode: PaddingMode,
+        align_corners: bool,
+    ):
+        super().__init__()
+        if hidden_dim % num_heads != 0:
+            raise ValueError(
+                f"Hidden dimension ({hidden_dim=}) should be divisible by number of heads ({num_heads=}).")
+        self.num_levels = num_levels
+        self.num_heads = num_heads
+        self.num_points = num_points
+        self.hidden_dim = hidden_dim
+        self.padding_mode = padding_mode
+        self.align_corners = align_corners
+        self.img_input_proj = nn.Linear(emb_dim, hidden_dim)
+        # per (head, level, point): 2 offset coordinates + 1 attention logit
+        self.query_input_proj = nn.Linear(emb_dim, num_heads * num_levels * num_points * 3)
+        self.query_output_proj = nn.Linear(hidden_dim, emb_dim)
+
+    def forward(
+        self,
+        img: torch.Tensor,
+        img_shapes: torch.Tensor,
+        queries: torch.Tensor,
+        reference_points: torch.Tensor,
+    ) -> torch.Tensor:
+        """
+        Args:
+            img: `[batch_size, num_image, emb_dim]` flattened pyramid.
+            img_shapes: `[num_levels, 2]` level shapes, (height, width).
+            queries: `[batch_size, num_queries, emb_dim]`.
+            reference_points: `[batch_size, num_queries, 2]` (x, y) or `[batch_size, num_queries, 4]` (cx, cy, w, h),
+                normalized to [0, 1].
+
+        Returns:
+            `[batch_size, num_queries, emb_dim]`.
+        """
+        batch, num_pixels, _ = img.shape
+        num_queries = queries.shape[1]
+        heads, levels, points = self.num_heads, self.num_levels, self.num_points
+
+        # offsets and logits come out of ONE projection, interleaved as (..., point, 3) (frontend.py:253-257)
+        projected = self.query_input_proj(queries).reshape(batch, num_queries, heads, levels, points, 3)
+        offsets, logits = projected[..., :2], projected[..., 2]
+        attention_weights = logits.reshape(batch, num_queries, heads, levels * points).softmax(dim=-1)
+        attention_weights = attention_weights.reshape(batch, num_queries, heads, levels, points)
+
+        value = self.img_input_proj(img).reshape(batch, num_pixels, heads, self.hidden_dim // heads)
+
+        anchor = reference_points[:, :, None, None, None, :]
+        coords = reference_points.shape[-1]
+        if coords == 2:
+            # NOTE: offsets are (x, y) while img_shapes rows are (h, w); the reference divides as-is
+            # (frontend.py:272-276) and drop-in parity keeps that.
+            sampling_points = anchor + offsets / img_shapes[:, None, :]
+        elif coords == 4:
+            sampling_points = anchor[..., :2] + offsets * anchor[..., 2:] / (2 * points)
+        else:
+            raise ValueError(f"`reference_points` should have the last dim either 2 or 4, but got {coords}.")
+
+        out = multiscale_deformable_attention(
+            value, img_shapes, sampling_points, attention_weights, self.padding_mode, self.align_corners)
+        return self.query_output_proj(out.reshape(batch, num_queries, self.hidden_dim))

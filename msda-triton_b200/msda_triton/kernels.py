@@ -1,0 +1,155 @@
+"""Operator boundary: tensors in, tensors out, compute in libmsda_b200.so (hand-written sm_100a CUDA).
+
+Mirrors the two wrapper functions that are the reference's kernel layer
+(``/root/reference/src/msda_triton/kernels.py:351-358`` forward, ``:556-564`` backward): same argument order and
+meaning, same ownership rule (this layer allocates outputs with torch's caching allocator; the kernels never
+allocate), launches on torch's current stream, never synchronises, reads ``img_shapes`` on the device.
+
+Differences from the reference wrappers, all deliberate:
+* outputs / gradients are always freshly allocated CONTIGUOUS tensors (the reference's ``zeros_like`` +
+  ``.contiguous()`` combination returns all-zero gradients for non-contiguous inputs, kernels.py:570-583);
+* ``grad_sampling_points`` / ``grad_attention_weights`` are not zero-filled first (every element is written);
+* gradients that autograd does not need are skipped (``needs`` argument);
+* bf16 storage is accepted; 16-bit storage accumulates ``grad_img`` in an fp32 scratch image.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Literal, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+_DTYPE_CODE = {
+    torch.float32: _lib.DTYPE_F32,
+    torch.float16: _lib.DTYPE_F16,
+    torch.bfloat16: _lib.DTYPE_BF16,
+    torch.float64: _lib.DTYPE_F64,
+}
+_PAD_CODE = {"zeros": _lib.PAD_ZEROS, "border": _lib.PAD_BORDER}
+
+_deterministic = False
+
+
+def set_deterministic(enabled: bool) -> None:
+    """Opt in to the bit-reproducible grad_img path (sorted-segment reduction instead of atomics)."""
+    global _deterministic
+    _deterministic = bool(enabled)
+
+
+def is_deterministic() -> bool:
+    return _deterministic or torch.are_deterministic_algorithms_enabled()
+
+
+def _dense(t: torch.Tensor) -> torch.Tensor:
+    """Contiguous and 16-byte aligned (vector loads); copies only when needed."""
+    t = t.contiguous()
+    if t.data_ptr() % 16 != 0:
+        t = t.clone(memory_format=torch.contiguous_format)
+    return t
+
+
+def _problem(img, img_shapes, pts, aw, padding_mode, align_corners) -> _lib.MsdaProblem:
+    if padding_mode not in _PAD_CODE:
+        raise ValueError(f"`padding_mode` should be 'border' or 'zeros', but got {padding_mode!r}.")
+    if img.dim() != 4 or pts.dim() != 6 or aw.dim() != 5 or img_shapes.dim() != 2:
+        raise ValueError(
+            "Expected img [B, I, H, C], img_shapes [L, 2], sampling_points [B, N, H, L, P, 2], attention_weights "
+            f"[B, N, H, L, P], but got {tuple(img.shape)}, {tuple(img_shapes.shape)}, {tuple(pts.shape)}, {tuple(aw.shape)}.")
+    B, Npix, H, D = img.shape
+    B2, Q, H2, L, K, two = pts.shape
+    if two != 2 or B2 != B or H2 != H or tuple(aw.shape) != (B, Q, H, L, K) or tuple(img_shapes.shape) != (L, 2):
+        raise ValueError(
+            f"Inconsistent shapes: img {tuple(img.shape)}, img_shapes {tuple(img_shapes.shape)}, "
+            f"sampling_points {tuple(pts.shape)}, attention_weights {tuple(aw.shape)}.")
+    if not (img.dtype == pts.dtype == aw.dtype) or img.dtype not in _DTYPE_CODE:
+        raise ValueError(f"img / sampling_points / attention_weights must share one dtype in {list(_DTYPE_CODE)}.")
+    return _lib.MsdaProblem(B, Npix, H, D, Q, L, K, _DTYPE_CODE[img.dtype], _PAD_CODE[padding_mode],
+                            int(bool(align_corners)), 0)
+
+
+def _shapes_i64(img_shapes: torch.Tensor) -> torch.Tensor:
+    if img_shapes.dtype != torch.int64:
+        img_shapes = img_shapes.to(torch.int64)
+    return img_shapes.contiguous()
+
+
+def _stream_ptr() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def b200_multi_scale_deformable_attention_fwd(
+    img: torch.Tensor,
+    img_shapes: torch.Tensor,
+    sampling_points: torch.Tensor,
+    attention_weights: torch.Tensor,
+    padding_mode: Literal["border", "zeros"],
+    align_corners: bool,
+) -> torch.Tensor:
+    """out[b,q,h,:] = sum_{l,k} w[b,q,h,l,k] * bilinear(img_l[b,:,h,:], p[b,q,h,l,k]); out dtype = img dtype."""
+    img, pts, aw = _dense(img), _dense(sampling_points), _dense(attention_weights)
+    shapes = _shapes_i64(img_shapes)
+    prob = _problem(img, shapes, pts, aw, padding_mode, align_corners)
+    out = torch.empty((prob.B, prob.Q, prob.H, prob.D), dtype=img.dtype, device=img.device)
+    with torch.cuda.device_of(img):
+        rc = _lib.get_lib().msda_forward(_ptr(out), _ptr(img), _ptr(shapes), _ptr(pts), _ptr(aw), ctypes.byref(prob),
+                                   _stream_ptr())
+    _lib.check(rc, "msda_forward")
+    return out
+
+
+def b200_multi_scale_deformable_attention_bwd(
+    out_grad: torch.Tensor,
+    img: torch.Tensor,
+    img_shapes: torch.Tensor,
+    sampling_points: torch.Tensor,
+    attention_weights: torch.Tensor,
+    padding_mode: Literal["border", "zeros"],
+    align_corners: bool,
+    needs: Sequence[bool] = (True, True, True),
+    deterministic: Optional[bool] = None,
+) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """Returns (img_grad, sampling_points_grad, attention_weights_grad); entries not in ``needs`` are None."""
+    img, pts, aw = _dense(img), _dense(sampling_points), _dense(attention_weights)
+    shapes = _shapes_i64(img_shapes)
+    prob = _problem(img, shapes, pts, aw, padding_mode, align_corners)
+    gout = _dense(out_grad.to(img.dtype))
+    if tuple(gout.shape) != (prob.B, prob.Q, prob.H, prob.D):
+        raise ValueError(f"out_grad has shape {tuple(gout.shape)}, expected {(prob.B, prob.Q, prob.H, prob.D)}.")
+    need_img, need_pts, need_aw = (bool(n) for n in needs)
+    flags = (_lib.BWD_NEED_IMG * need_img) | (_lib.BWD_NEED_POINTS * need_pts) | (_lib.BWD_NEED_WEIGHTS * need_aw)
+    if deterministic is None:
+        deterministic = is_deterministic()
+    if deterministic and need_img:
+        flags |= _lib.BWD_DETERMINISTIC
+    gimg = torch.empty(img.shape, dtype=img.dtype, device=img.device) if need_img else None
+    gpts = torch.empty(pts.shape, dtype=pts.dtype, device=img.device) if need_pts else None
+    gaw = torch.empty(aw.shape, dtype=aw.dtype, device=img.device) if need_aw else None
+    with torch.cuda.device_of(img):
+        ws_bytes = int(_lib.get_lib().msda_backward_workspace_bytes(ctypes.byref(prob), flags))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=img.device) if ws_bytes else None
+        rc = _lib.get_lib().msda_backward(_ptr(gimg), _ptr(gpts), _ptr(gaw), _ptr(gout), _ptr(img), _ptr(shapes), _ptr(pts),
+                                    _ptr(aw), ctypes.byref(prob), flags, _ptr(ws), ws_bytes, _stream_ptr())
+    _lib.check(rc, "msda_backward")
+    return gimg, gpts, gaw
+
+
+def level_table(img_shapes: torch.Tensor, num_pixels: int) -> torch.Tensor:
+    """Device-side level preprocessing: int32 [L+1, 4] rows {h, w, offset, 0} + {sum, Npix, sum==Npix, 0}."""
+    shapes = _shapes_i64(img_shapes)
+    L = shapes.shape[0]
+    table = torch.empty((L + 1, 4), dtype=torch.int32, device=shapes.device)
+    with torch.cuda.device_of(shapes):
+        rc = _lib.get_lib().msda_level_table(_ptr(table), _ptr(shapes), L, int(num_pixels), _stream_ptr())
+    _lib.check(rc, "msda_level_table")
+    return table
+
+
+# The reference's names for this layer (kernels.py:351, :556) resolve to the CUDA implementation.
+triton_multi_scale_deformable_attention_fwd = b200_multi_scale_deformable_attention_fwd
+triton_multi_scale_deformable_attention_bwd = b200_multi_scale_deformable_attention_bwd

@@ -1,0 +1,272 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libmsda_b200.so) against the CPU oracle and against the
+golden vectors produced by the unmodified reference.  Tolerances are BASELINE.json's:
+   fp32 forward   rtol 1e-5 / atol 1e-6
+   fp32 backward  rtol 1e-4 (atol 1e-5 * max|ref| per tensor -- elements near zero need an absolute floor)
+   fp64           1e-8 (the reference's own bar, tests/test_msda.py:23-26), in practice ~1e-13
+   fp16 / bf16    storage bounds stated in test_16bit_storage.
+"""
+import itertools
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from util import BENCH_PYRAMID, DETR_PYRAMID, assert_close, make_inputs, to_np
+
+pytestmark = pytest.mark.gpu
+
+MODES = list(itertools.product(("zeros", "border"), (False, True)))
+
+
+@pytest.fixture(scope="module")
+def K():
+    from msda_triton import kernels
+    assert torch.cuda.is_available()
+    return kernels
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    from oracle import msda_oracle
+    return msda_oracle
+
+
+def run_cuda(K, img, shapes, pts, aw, go, pm, ac, **kw):
+    dev = "cuda"
+    a, s, p, w, g = (t.to(dev) for t in (img, shapes, pts, aw, go))
+    out = K.b200_multi_scale_deformable_attention_fwd(a, s, p, w, pm, ac)
+    gi, gp, ga = K.b200_multi_scale_deformable_attention_bwd(g, a, s, p, w, pm, ac, **kw)
+    torch.cuda.synchronize()
+    return out, gi, gp, ga
+
+
+def check_against(test, ref, dtype, what, gpts_outliers=0):
+    out, gi, gp, ga = (to_np(t) for t in test)
+    rout, rgi, rgp, rga = ref
+    if dtype == torch.float32:
+        assert_close(out, rout, 1e-5, 1e-6, f"{what} out")
+        assert_close(gi, rgi, 1e-4, 1e-5 * np.abs(rgi).max(), f"{what} grad_img")
+        assert_close(ga, rga, 1e-4, 1e-5 * np.abs(rga).max(), f"{what} grad_attention_weights")
+        assert_close(gp, rgp, 1e-4, 1e-5 * np.abs(rgp).max(), f"{what} grad_sampling_points", gpts_outliers)
+    else:
+        assert_close(out, rout, 1e-8, 1e-8, f"{what} out")
+        assert_close(gi, rgi, 1e-8, 1e-8, f"{what} grad_img")
+        assert_close(ga, rga, 1e-8, 1e-8, f"{what} grad_attention_weights")
+        assert_close(gp, rgp, 1e-8, 1e-8 * max(1.0, np.abs(rgp).max()), f"{what} grad_sampling_points", gpts_outliers)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# golden vectors from the unmodified reference (Triton kernels under the CPU interpreter)
+# ---------------------------------------------------------------------------------------------------------------------
+GOLD = sorted(p for p in GOLDEN.glob("*.npz") if not p.name.endswith("float16.npz"))
+
+
+@pytest.mark.parametrize("path", GOLD, ids=lambda p: p.stem)
+@pytest.mark.parametrize("pm,ac", MODES)
+def test_golden_reference_kernels(K, path, pm, ac):
+    g = np.load(path)
+    tag = f"{pm}_{int(ac)}"
+    t = {k: torch.from_numpy(g[k]) for k in ("img", "img_shapes", "sampling_points", "attention_weights", "out_grad")}
+    test = run_cuda(K, t["img"], t["img_shapes"], t["sampling_points"], t["attention_weights"], t["out_grad"], pm, ac)
+    ref = tuple(g[f"triton_{n}_{tag}"] for n in ("out", "gimg", "gpts", "gaw"))
+    check_against(test, ref, t["img"].dtype, f"{path.stem} {tag}")
+
+
+@pytest.mark.parametrize("path", sorted(GOLDEN.glob("*float16.npz")), ids=lambda p: p.stem)
+@pytest.mark.parametrize("pm,ac", MODES)
+def test_golden_fp16_reference_kernels(K, path, pm, ac):
+    """The reference computes fp16 IN fp16 (coordinates included), we compute in fp32 from the same fp16 inputs, so
+    agreement is bounded by the reference's own fp16 rounding: its test bar is atol=rtol=1e-1 (tests/test_msda.py:16-18).
+    The coordinate rounding (x*w-0.5 in fp16) moves samples by up to 1/32 px, hence the looser gradient bars."""
+    g = np.load(path)
+    tag = f"{pm}_{int(ac)}"
+    t = {k: torch.from_numpy(g[k]) for k in ("img", "img_shapes", "sampling_points", "attention_weights", "out_grad")}
+    out, gi, gp, ga = run_cuda(K, t["img"], t["img_shapes"], t["sampling_points"], t["attention_weights"],
+                               t["out_grad"], pm, ac)
+    assert out.dtype == torch.float16
+    assert_close(to_np(out), g[f"triton_out_{tag}"].astype(np.float64), 1e-1, 1e-1, "fp16 out")
+    assert_close(to_np(gi), g[f"triton_gimg_{tag}"].astype(np.float64), 1e-1, 1e-1, "fp16 grad_img")
+    assert_close(to_np(ga), g[f"triton_gaw_{tag}"].astype(np.float64), 1e-1, 1e-1, "fp16 grad_aw")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# oracle parity on the reference's own fixture shapes (tests/test_msda.py:30-47, :162-167) and BASELINE configs
+# ---------------------------------------------------------------------------------------------------------------------
+CASES = {
+    # name: (B, Q, H, D, shapes, K, points, weights)
+    "ref_fixture_k3": (4, 1000, 8, 32, BENCH_PYRAMID, 3, "unit", "softmax_k"),        # generic kernel (L*K = 12)
+    "ref_module_d4_k8": (4, 1000, 8, 4, BENCH_PYRAMID, 8, "far", "softmax_lk"),       # D=4, far out of bounds
+    "readme_c1": (2, 900, 8, 32, BENCH_PYRAMID, 4, "unit", "softmax_lk"),             # tuned kernel
+    "readme_c1_wide": (2, 900, 8, 32, BENCH_PYRAMID, 4, "wide", "softmax_k"),
+    "detr_small": (1, 777, 8, 32, [(25, 42), (13, 21), (7, 11), (4, 6)], 4, "wide", "softmax_lk"),
+    "d64": (2, 333, 4, 64, [(20, 30), (10, 15), (5, 8), (3, 4)], 4, "wide", "softmax_lk"),
+    "odd_everything": (3, 61, 5, 6, [(9, 7), (5, 4), (2, 3)], 5, "wide", "softmax_lk"),
+    "one_level_one_point": (2, 50, 3, 16, [(7, 9)], 1, "far", "softmax_lk"),
+    "wide_channels": (1, 40, 2, 200, [(6, 6), (3, 3)], 2, "wide", "softmax_lk"),      # D > 32*4: channel chunks
+    "many_points": (1, 30, 2, 8, [(6, 6), (3, 3), (2, 2)], 19, "wide", "softmax_lk"), # L*K = 57 > 32 lanes
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["f32", "f64"])
+@pytest.mark.parametrize("pm,ac", MODES)
+def test_oracle_parity(K, oracle, name, dtype, pm, ac):
+    B, Q, H, D, shapes, Kp, points, weights = CASES[name]
+    img, s, pts, aw, go = make_inputs(B, Q, H, D, shapes, Kp, dtype=dtype, seed=7, points=points, weights=weights)
+    test = run_cuda(K, img, s, pts, aw, go, pm, ac)
+    ref = (oracle.forward(img, s, pts, aw, pm, ac),) + oracle.backward(go, img, s, pts, aw, pm, ac)
+    check_against(test, ref, dtype, f"{name} {pm}/{ac}")
+
+
+@pytest.mark.parametrize("pm,ac", MODES)
+def test_tuned_equals_generic(K, pm, ac):
+    """The tuned (persistent, (b,h)-major) kernels and the generic kernels implement the same arithmetic per corner;
+    only summation order differs."""
+    img, s, pts, aw, go = make_inputs(2, 500, 8, 32, BENCH_PYRAMID, 4, seed=3, points="wide")
+    tuned = run_cuda(K, img, s, pts, aw, go, pm, ac)
+    os.environ["MSDA_B200_FORCE_GENERIC"] = "1"
+    try:
+        generic = run_cuda(K, img, s, pts, aw, go, pm, ac)
+    finally:
+        os.environ.pop("MSDA_B200_FORCE_GENERIC")
+    for a, b, what in zip(tuned, generic, ("out", "grad_img", "grad_points", "grad_weights")):
+        b = to_np(b)
+        assert_close(to_np(a), b, 1e-5, 2e-6 * max(1.0, np.abs(b).max()), what)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 16-bit storage
+# ---------------------------------------------------------------------------------------------------------------------
+def _bounds(dtype):
+    # one rounding of the result to storage precision (eps/2 relative) + fp32 accumulation noise
+    eps = 2.0 ** -10 if dtype == torch.float16 else 2.0 ** -7
+    return eps
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
+@pytest.mark.parametrize("D,Kp", [(32, 4), (64, 4), (32, 3), (4, 8)])
+@pytest.mark.parametrize("pm,ac", MODES)
+def test_16bit_storage_bounds(K, oracle, dtype, D, Kp, pm, ac):
+    """16-bit STORAGE, fp32 compute: against the fp64 oracle evaluated on the same (already rounded) inputs every
+    output may differ by one storage rounding: |err| <= eps*|ref| + eps*1e-2*max|ref| with eps = 2^-10 (fp16) or
+    2^-7 (bf16).  (The reference computes fp16 in fp16 and accepts 1e-1.)"""
+    img, s, pts, aw, go = make_inputs(2, 300, 8, D, BENCH_PYRAMID, Kp, dtype=dtype, seed=11, points="wide",
+                                      weights="softmax_lk")
+    out, gi, gp, ga = run_cuda(K, img, s, pts, aw, go, pm, ac)
+    assert out.dtype == dtype and gi.dtype == dtype and gp.dtype == dtype and ga.dtype == dtype
+    rout = oracle.forward(img, s, pts, aw, pm, ac)
+    rgi, rgp, rga = oracle.backward(go, img, s, pts, aw, pm, ac)
+    eps = _bounds(dtype)
+    for t, r, what in ((out, rout, "out"), (gi, rgi, "grad_img"), (gp, rgp, "grad_points"), (ga, rga, "grad_weights")):
+        assert_close(to_np(t), r, eps, eps * 1e-2 * np.abs(r).max(), f"{dtype} {what}")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE.json full sizes: direct oracle comparison + size-independent properties
+# ---------------------------------------------------------------------------------------------------------------------
+FULL = {
+    "bench_q10k": (4, 10000, 8, 32, BENCH_PYRAMID, 4),
+    "detr_encoder": (2, 22223, 8, 32, DETR_PYRAMID, 4),
+}
+
+
+@pytest.mark.parametrize("name", list(FULL))
+@pytest.mark.parametrize("pm,ac", [("border", True), ("zeros", False)])
+def test_full_size_oracle_and_properties(K, oracle, name, pm, ac):
+    B, Q, H, D, shapes, Kp = FULL[name]
+    img, s, pts, aw, go = make_inputs(B, Q, H, D, shapes, Kp, seed=5, points="unit", weights="softmax_k")
+    out, gi, gp, ga = run_cuda(K, img, s, pts, aw, go, pm, ac)
+    ref = (oracle.forward(img, s, pts, aw, pm, ac),) + oracle.backward(go, img, s, pts, aw, pm, ac)
+    # a handful of floor-cell flips are tolerated in grad_sampling_points at this size (none expected: the
+    # coordinate arithmetic is bit-identical to the oracle's)
+    check_against((out, gi, gp, ga), ref, torch.float32, name, gpts_outliers=4)
+
+    # property 1: linearity in img  (f(2*img + img2) = 2 f(img) + f(img2))
+    img2 = torch.roll(img, 1, dims=1)
+    dev = "cuda"
+    f = lambda x: K.b200_multi_scale_deformable_attention_fwd(x.to(dev), s.to(dev), pts.to(dev), aw.to(dev), pm, ac)  # noqa: E731
+    lhs = f(2 * img + img2)
+    rhs = 2 * out + f(img2)
+    assert_close(to_np(lhs), to_np(rhs), 1e-5, 1e-5, "linearity")
+
+    # property 2 (border): bilinear weights sum to 1, so sum_pixels grad_img[b,:,h,d] = sum_q go[b,q,h,d] * sum_lk w
+    if pm == "border":
+        lhs = gi.double().sum(dim=1)                                                       # [B, H, D]
+        rhs = (go.double().to(dev) * aw.double().to(dev).sum(dim=(3, 4))[..., None]).sum(dim=1)
+        assert_close(to_np(lhs), to_np(rhs), 1e-5, 1e-4, "grad_img checksum")
+
+    # property 3: grad_attention_weights is the directional derivative of out w.r.t. each weight:
+    #   sum_{l,k} w * gaw = <go, out>  per unit
+    lhs = (aw.double().to(dev) * ga.double()).sum(dim=(3, 4))
+    rhs = (go.double().to(dev) * out.double()).sum(dim=-1)
+    assert_close(to_np(lhs), to_np(rhs), 1e-4, 1e-4, "euler identity")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# edge cases
+# ---------------------------------------------------------------------------------------------------------------------
+def test_empty_inputs(K):
+    img, s, pts, aw, go = make_inputs(2, 0, 4, 32, BENCH_PYRAMID, 4)
+    out, gi, gp, ga = run_cuda(K, img, s, pts, aw, go, "zeros", False)
+    assert out.shape == (2, 0, 4, 32) and gp.shape == pts.shape and ga.shape == aw.shape
+    assert gi.shape == img.shape and float(gi.abs().max()) == 0.0
+
+
+def test_needs_subset(K, oracle):
+    img, s, pts, aw, go = make_inputs(2, 200, 8, 32, BENCH_PYRAMID, 4, seed=2)
+    ref = oracle.backward(go, img, s, pts, aw, "border", True)
+    for needs in itertools.product((False, True), repeat=3):
+        got = run_cuda(K, img, s, pts, aw, go, "border", True, needs=needs)[1:]
+        for n, t, r, what in zip(needs, got, ref, ("grad_img", "grad_points", "grad_weights")):
+            if n:
+                assert_close(to_np(t), r, 1e-4, 1e-5 * np.abs(r).max(), f"needs={needs} {what}")
+            else:
+                assert t is None
+
+
+def test_noncontiguous_and_misaligned(K, oracle):
+    img, s, pts, aw, go = make_inputs(2, 100, 8, 32, BENCH_PYRAMID, 4, seed=9)
+    dev = "cuda"
+    img_nc = img.to(dev).permute(0, 2, 1, 3).contiguous().permute(0, 2, 1, 3)            # strided view
+    flat = torch.empty(pts.numel() + 1, device=dev)
+    flat[1:] = pts.to(dev).reshape(-1)
+    pts_mis = flat[1:].view(pts.shape)                                                   # 4-byte aligned only
+    assert not img_nc.is_contiguous() and pts_mis.data_ptr() % 16 != 0
+    out = K.b200_multi_scale_deformable_attention_fwd(img_nc, s.to(dev), pts_mis, aw.to(dev), "zeros", False)
+    gi, gp, ga = K.b200_multi_scale_deformable_attention_bwd(go.to(dev), img_nc, s.to(dev), pts_mis, aw.to(dev),
+                                                             "zeros", False)
+    ref = (oracle.forward(img, s, pts, aw, "zeros", False),) + oracle.backward(go, img, s, pts, aw, "zeros", False)
+    check_against((out, gi, gp, ga), ref, torch.float32, "noncontiguous")
+    assert gi.is_contiguous() and float(gi.abs().max()) > 0     # the reference returns zeros here (kernels.py:570-583)
+
+
+def test_level_table_on_device(K, oracle):
+    s = torch.tensor(DETR_PYRAMID, device="cuda")
+    t = K.level_table(s, 22223).cpu().numpy()
+    ref = oracle.level_table(np.array(DETR_PYRAMID))
+    assert (t[:4, :3] == ref).all()
+    assert t[4].tolist() == [22223, 22223, 1, 0]
+    assert K.level_table(s, 22222).cpu().numpy()[4, 2] == 0
+
+
+def test_int32_shapes_and_cpu_shapes(K, oracle):
+    import msda_triton
+    img, s, pts, aw, go = make_inputs(1, 64, 2, 32, BENCH_PYRAMID, 4, seed=4)
+    ref = oracle.forward(img, s, pts, aw, "border", False)
+    out = K.b200_multi_scale_deformable_attention_fwd(img.cuda(), s.to(torch.int32).cuda(), pts.cuda(), aw.cuda(),
+                                                      "border", False)
+    assert_close(to_np(out), ref, 1e-5, 1e-6, "int32 shapes")
+    out = msda_triton.multiscale_deformable_attention(img.cuda(), s, pts.cuda(), aw.cuda(), "border", False)
+    assert_close(to_np(out), ref, 1e-5, 1e-6, "cpu shapes through the dispatcher")
+
+
+def test_bad_arguments_raise(K):
+    img, s, pts, aw, go = make_inputs(1, 8, 2, 32, BENCH_PYRAMID, 4)
+    with pytest.raises(ValueError):
+        K.b200_multi_scale_deformable_attention_fwd(img.cuda(), s.cuda(), pts.cuda(), aw.cuda(), "reflect", False)
+    with pytest.raises(ValueError):
+        K.b200_multi_scale_deformable_attention_fwd(img.cuda(), s.cuda(), pts.cuda()[:, :, :1], aw.cuda(), "zeros", False)
+    with pytest.raises(ValueError):
+        K.b200_multi_scale_deformable_attention_fwd(img.cuda().half(), s.cuda(), pts.cuda(), aw.cuda(), "zeros", False)
