@@ -182,10 +182,11 @@ int msda_backward(void *grad_img, void *grad_points, void *grad_weights, const v
     if ((flags & MSDA_BWD_NEED_ALL) == 0) return MSDA_OK;
     const bool need_img = flags & MSDA_BWD_NEED_IMG, need_pts = flags & MSDA_BWD_NEED_POINTS,
                need_aw = flags & MSDA_BWD_NEED_WEIGHTS;
-    if ((need_img && !grad_img) || (need_pts && !grad_points) || (need_aw && !grad_weights))
-        return fail(MSDA_ERR_NULL_POINTER, "msda_backward: a requested gradient buffer is NULL");
     const size_t es = dtype_size(prob->dtype);
     const size_t img_elems = (size_t)prob->B * prob->Npix * prob->H * prob->D;
+    const bool no_units = prob->B == 0 || prob->Q == 0;  // empty tensors legitimately have NULL data pointers
+    if ((need_img && !grad_img && img_elems > 0) || (!no_units && ((need_pts && !grad_points) || (need_aw && !grad_weights))))
+        return fail(MSDA_ERR_NULL_POINTER, "msda_backward: a requested gradient buffer is NULL");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     DeviceInfo dev;
     rc = device_info(&dev);
@@ -197,7 +198,7 @@ int msda_backward(void *grad_img, void *grad_points, void *grad_weights, const v
     size_t accum_bytes = img_elems * es;
     if (staged) {
         const size_t want = msda_backward_workspace_bytes(prob, flags);
-        if (!workspace || workspace_bytes < want)
+        if ((!workspace && want > 0) || workspace_bytes < want)
             return fail(MSDA_ERR_WORKSPACE, "msda_backward: workspace of %zu bytes required, got %zu", want,
                         workspace_bytes);
         if (!aligned(workspace, 16)) return fail(MSDA_ERR_WORKSPACE, "msda_backward: workspace must be 16-byte aligned");

@@ -10,7 +10,6 @@
 // [0,1] coordinate, hence the (w-1)|w scale factor.
 #include "msda_common.cuh"
 #include "msda_launch.h"
-#include "msda_tiled.cuh"
 
 namespace msda {
 
@@ -223,198 +222,6 @@ cudaError_t launch_backward_generic(const KernelArgs &a, int dtype, int vec, int
     return cudaErrorInvalidValue;
 }
 
-
-// ---------------------------------------------------------------------------------------------------------------
-// Tuned backward: same persistent (b,h)-major schedule and lane layout as the tuned forward.
-//
-// Per sampling point every lane forms, over its VEC channels, the four corner dot products <go, v_c>; from them the
-// three per-point partials (grad weight, d/dx, d/dy).  The 3*LK partials of a unit live in registers until the
-// end of the unit and are then reduced across the LANES lanes with a TRANSPOSING butterfly (each step halves the
-// values a lane keeps), which costs 3*LK*(1 - 1/LANES) shuffles instead of 3*LK*log2(LANES) and leaves lane j
-// holding exactly the PPL points it loaded -- so the grad_points / grad_weights stores are the same coalesced
-// vector stores as the loads.  grad_img goes out as one REDG.E.ADD.F32x4 per lane per valid corner.
-// ---------------------------------------------------------------------------------------------------------------
-template <int N, int STEP> __device__ __forceinline__ void transpose_reduce(float (&part)[N], const int j) {
-    // lanes with bit STEP clear keep the lower half, their partners (j ^ STEP) the upper half
-    constexpr int HALF = N / 2;
-    const bool upper = (j & STEP) != 0;
-#pragma unroll
-    for (int k = 0; k < HALF; ++k) {
-        const float keep = upper ? part[k + HALF] : part[k];
-        const float send = upper ? part[k] : part[k + HALF];
-        part[k] = keep + __shfl_xor_sync(0xffffffffu, send, STEP);
-    }
-    if constexpr (STEP > 1) {
-        float(&lower)[HALF] = reinterpret_cast<float(&)[HALF]>(part);
-        transpose_reduce<HALF, STEP / 2>(lower, j);
-    }
-}
-
-template <typename T, int LANES, int LK, bool BORDER>
-__global__ void __launch_bounds__(kTiledThreads, 1)
-    msda_bwd_tiled_kernel(const KernelArgs a, const int tiles_per_bh, const long long total_tiles) {
-    using Cfg = TiledCfg<T, LANES, LK>;
-    constexpr int VEC = Cfg::VEC, G = Cfg::G, PPL = Cfg::PPL;
-    constexpr int NB = 2;  // points per gather batch (8 gathers in flight per lane; registers also hold 3*LK partials)
-    static_assert(LANES % NB == 0, "batch must divide the group");
-
-    __shared__ Level s_lv[LK];
-    build_level_table(s_lv, a.shapes, a.L);
-
-    const T *__restrict__ img = static_cast<const T *>(a.img);
-    const T *__restrict__ pts = static_cast<const T *>(a.pts);
-    const T *__restrict__ aw = static_cast<const T *>(a.aw);
-    const T *__restrict__ gout = static_cast<const T *>(a.gout);
-    float *__restrict__ gimg = static_cast<float *>(a.gimg);
-    T *__restrict__ gpts = static_cast<T *>(a.gpts);
-    T *__restrict__ gaw = static_cast<T *>(a.gaw);
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int j = lane % LANES, g = lane / LANES;
-    const bool align = a.align != 0;
-    const bool need_img = (a.flags & kNeedImg) != 0, need_pts = (a.flags & kNeedPts) != 0,
-               need_aw = (a.flags & kNeedAw) != 0;
-    const size_t row_stride = (size_t)a.H * a.D;
-
-    const long long t_begin = total_tiles * blockIdx.x / gridDim.x;
-    const long long t_end = total_tiles * (blockIdx.x + 1) / gridDim.x;
-
-    for (long long tile = t_begin + warp; tile < t_end; tile += nwarps) {
-        const TileUnit tu = decode_tile(tile, tiles_per_bh, g, G, a);
-        const T *__restrict__ img_lane = img + tu.bh_off + j * VEC;
-        float *__restrict__ gimg_lane = gimg + tu.bh_off + j * VEC;
-        const bool scatter = need_img && tu.live;
-
-        float xy[2 * PPL], wa[PPL], sx[PPL], sy[PPL];
-        load_vec<T, 2 * PPL>(pts + ((size_t)tu.u * LK + j * PPL) * 2, xy);
-        load_vec<T, PPL>(aw + (size_t)tu.u * LK + j * PPL, wa);
-        Tap<float> tap[PPL];
-#pragma unroll
-        for (int pp = 0; pp < PPL; ++pp) {
-            const Level lv = s_lv[(j * PPL + pp) / a.K];
-            tap[pp] = locate<float>(xy[2 * pp], xy[2 * pp + 1], lv, BORDER, align);
-            sx[pp] = align ? (float)(lv.w - 1) : (float)lv.w;
-            sy[pp] = align ? (float)(lv.h - 1) : (float)lv.h;
-        }
-        float go[VEC];
-        load_vec<T, VEC>(gout + (size_t)tu.u * a.D + j * VEC, go);
-
-        // part[(jj*PPL + pp)*3 + {0,1,2}] : point jj*PPL+pp  ->  {grad weight, d/dx, d/dy} partial over my channels
-        float part[3 * LK];
-
-#pragma unroll
-        for (int pp = 0; pp < PPL; ++pp) {
-#pragma unroll
-            for (int jj0 = 0; jj0 < LANES; jj0 += NB) {
-                uint4 raw[NB][4];
-                float fx[NB], fy[NB], fw[NB];
-                size_t off[NB][4];
-                unsigned msk[NB];
-#pragma unroll
-                for (int n = 0; n < NB; ++n) {
-                    const int src = jj0 + n;
-                    const int row00 = __shfl_sync(0xffffffffu, tap[pp].row00, src, LANES);
-                    const int pack = __shfl_sync(0xffffffffu, tap[pp].pack, src, LANES);
-                    fx[n] = __shfl_sync(0xffffffffu, tap[pp].dx, src, LANES);
-                    fy[n] = __shfl_sync(0xffffffffu, tap[pp].dy, src, LANES);
-                    fw[n] = __shfl_sync(0xffffffffu, wa[pp], src, LANES);
-                    const int step_y = pack & kPackDyMask;
-                    const int step_x = (pack >> kPackDxBit) & 1;
-                    msk[n] = BORDER ? 0xFu : ((unsigned)(pack >> kPackMaskShift) & 0xFu);
-                    off[n][0] = (size_t)row00 * row_stride;
-                    off[n][1] = off[n][0] + (size_t)step_x * row_stride;
-                    off[n][2] = off[n][0] + (size_t)step_y * row_stride;
-                    off[n][3] = off[n][2] + (size_t)step_x * row_stride;
-                    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        raw[n][c] = (BORDER || ((msk[n] >> c) & 1u)) ? gather_row<T>(img_lane + off[n][c]) : zero;
-                }
-#pragma unroll
-                for (int n = 0; n < NB; ++n) {
-                    const float dx = fx[n], dy = fy[n];
-                    float bw[4];  // bilinear weights of corners 00, 01, 10, 11
-                    bw[1] = (1.0f - dy) * dx;
-                    bw[0] = (1.0f - dy) - bw[1];
-                    bw[3] = dy * dx;
-                    bw[2] = dy - bw[3];
-                    float d[4];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        float v[VEC];
-                        widen_row<T, VEC>(raw[n][c], v);
-                        float acc = 0.0f;
-#pragma unroll
-                        for (int e = 0; e < VEC; ++e) acc = fmaf(go[e], v[e], acc);
-                        d[c] = acc;
-                        if (scatter && (BORDER || ((msk[n] >> c) & 1u))) {
-                            const float s = fw[n] * bw[c];
-                            float gv[VEC];
-#pragma unroll
-                            for (int e = 0; e < VEC; ++e) gv[e] = go[e] * s;
-                            red_add_vec<VEC>(gimg_lane + off[n][c], gv);
-                        }
-                    }
-                    const int pidx = (jj0 + n) * PPL + pp;
-                    part[3 * pidx + 0] = bw[0] * d[0] + bw[1] * d[1] + bw[2] * d[2] + bw[3] * d[3];
-                    part[3 * pidx + 1] = (1.0f - dy) * (d[1] - d[0]) + dy * (d[3] - d[2]);
-                    part[3 * pidx + 2] = (1.0f - dx) * (d[2] - d[0]) + dx * (d[3] - d[1]);
-                }
-            }
-        }
-
-        // ---- reduce over the LANES lanes; lane j ends with points [j*PPL, (j+1)*PPL) in part[0 .. 3*PPL) ----
-        transpose_reduce<3 * LK, LANES / 2>(part, j);
-
-        if (tu.live) {
-            if (need_aw) {
-                float gw[PPL];
-#pragma unroll
-                for (int pp = 0; pp < PPL; ++pp) gw[pp] = part[3 * pp + 0];
-                store_vec<T, PPL>(gaw + (size_t)tu.u * LK + j * PPL, gw);
-            }
-            if (need_pts) {
-                float gp[2 * PPL];
-#pragma unroll
-                for (int pp = 0; pp < PPL; ++pp) {
-                    gp[2 * pp + 0] = part[3 * pp + 1] * (wa[pp] * sx[pp]);
-                    gp[2 * pp + 1] = part[3 * pp + 2] * (wa[pp] * sy[pp]);
-                }
-                store_vec<T, 2 * PPL>(gpts + ((size_t)tu.u * LK + j * PPL) * 2, gp);
-            }
-        }
-    }
-}
-
-template <typename T, int LANES, int LK>
-static cudaError_t launch_tiled_t(const KernelArgs &a, int sm_count, cudaStream_t st) {
-    constexpr int G = TiledCfg<T, LANES, LK>::G;
-    const int tiles_per_bh = (a.Q + G - 1) / G;
-    const long long total_tiles = (long long)a.B * a.H * tiles_per_bh;
-    const int warps = kTiledThreads / 32;
-    long long want = (total_tiles + warps - 1) / warps;
-    const int grid = (int)(want < sm_count ? (want < 1 ? 1 : want) : sm_count);
-    if (a.border)
-        msda_bwd_tiled_kernel<T, LANES, LK, true><<<grid, kTiledThreads, 0, st>>>(a, tiles_per_bh, total_tiles);
-    else
-        msda_bwd_tiled_kernel<T, LANES, LK, false><<<grid, kTiledThreads, 0, st>>>(a, tiles_per_bh, total_tiles);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_backward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st) {
-    if (a.LK != 16 || a.L > 16) return cudaErrorNotSupported;
-    if (dtype == 0) {
-        if (a.D == 32) return launch_tiled_t<float, 8, 16>(a, sm_count, st);
-        if (a.D == 64) return launch_tiled_t<float, 16, 16>(a, sm_count, st);
-    } else if (dtype == 1) {
-        if (a.D == 32) return launch_tiled_t<__half, 4, 16>(a, sm_count, st);
-        if (a.D == 64) return launch_tiled_t<__half, 8, 16>(a, sm_count, st);
-    } else if (dtype == 2) {
-        if (a.D == 32) return launch_tiled_t<__nv_bfloat16, 4, 16>(a, sm_count, st);
-        if (a.D == 64) return launch_tiled_t<__nv_bfloat16, 8, 16>(a, sm_count, st);
-    }
-    return cudaErrorNotSupported;
-}
 
 // ---------------------------------------------------------------------------------------------------------------
 // 16-bit storage epilogue: grad_img[T] = round(accumulation image[fp32]).

@@ -2,7 +2,7 @@
 //
 // Replaces the reference's Triton forward (src/msda_triton/kernels.py:267-348, launched from :351-379).
 //
-// Work decomposition (both kernels): one "unit" = one output row (b,q,h).  `lanes` lanes of a warp cooperate on a
+// Work decomposition: one "unit" = one output row (b,q,h).  `lanes` lanes of a warp cooperate on a
 // unit; each lane owns VEC consecutive channels and gathers them with ONE vector load per bilinear corner
 // (128-bit when D*sizeof(T) allows).  The coordinate math of the L*K sampling points is NOT replicated across the
 // lanes: lane j resolves points j, j+lanes, ... and the results are exchanged with warp shuffles.
@@ -10,7 +10,6 @@
 // reduction and no tensor-core use -- the op is a gather (about 0.6 flop per byte).
 #include "msda_common.cuh"
 #include "msda_launch.h"
-#include "msda_tiled.cuh"
 
 namespace msda {
 
@@ -151,143 +150,6 @@ cudaError_t launch_forward_generic(const KernelArgs &a, int dtype, int vec, int 
         case 3: return dispatch_vec<double>(a, vec, sm_count, st);
     }
     return cudaErrorInvalidValue;
-}
-
-
-// ---------------------------------------------------------------------------------------------------------------
-// Tuned kernel: L*K == LK (16), row of LANES x 128 bit, persistent (b,h)-major schedule (see msda_tiled.cuh).
-// Per warp iteration: G = 32/LANES units.  Each lane resolves PPL = LK/LANES points, then the group walks the LK
-// points in batches of NB: 5 shuffles + 4 independent 128-bit gathers per point, 4*NB gathers in flight per lane.
-// ---------------------------------------------------------------------------------------------------------------
-template <typename T, int LANES, int LK, bool BORDER>
-__global__ void __launch_bounds__(kTiledThreads, 1)
-    msda_fwd_tiled_kernel(const KernelArgs a, const int tiles_per_bh, const long long total_tiles) {
-    using Cfg = TiledCfg<T, LANES, LK>;
-    constexpr int VEC = Cfg::VEC, G = Cfg::G, PPL = Cfg::PPL;
-    constexpr int NB = 4;  // points per gather batch
-    static_assert(LANES % NB == 0, "batch must divide the group");
-
-    __shared__ Level s_lv[LK];
-    build_level_table(s_lv, a.shapes, a.L);
-
-    const T *__restrict__ img = static_cast<const T *>(a.img);
-    const T *__restrict__ pts = static_cast<const T *>(a.pts);
-    const T *__restrict__ aw = static_cast<const T *>(a.aw);
-    T *__restrict__ out = static_cast<T *>(a.out);
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int j = lane % LANES, g = lane / LANES;
-    const bool align = a.align != 0;
-    const size_t row_stride = (size_t)a.H * a.D;
-
-    const long long t_begin = total_tiles * blockIdx.x / gridDim.x;
-    const long long t_end = total_tiles * (blockIdx.x + 1) / gridDim.x;
-
-    for (long long tile = t_begin + warp; tile < t_end; tile += nwarps) {
-        const TileUnit tu = decode_tile(tile, tiles_per_bh, g, G, a);
-        const T *__restrict__ img_lane = img + tu.bh_off + j * VEC;
-
-        // ---- resolve this lane's PPL points ----
-        float xy[2 * PPL], wa[PPL];
-        load_vec<T, 2 * PPL>(pts + ((size_t)tu.u * LK + j * PPL) * 2, xy);
-        load_vec<T, PPL>(aw + (size_t)tu.u * LK + j * PPL, wa);
-        Tap<float> tap[PPL];
-#pragma unroll
-        for (int pp = 0; pp < PPL; ++pp) {
-            const Level lv = s_lv[(j * PPL + pp) / a.K];
-            tap[pp] = locate<float>(xy[2 * pp], xy[2 * pp + 1], lv, BORDER, align);
-        }
-
-        float acc[VEC];
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) acc[e] = 0.0f;
-
-#pragma unroll
-        for (int pp = 0; pp < PPL; ++pp) {
-#pragma unroll
-            for (int jj0 = 0; jj0 < LANES; jj0 += NB) {
-                uint4 raw[NB][4];
-                float fx[NB], fy[NB], fw[NB];
-#pragma unroll
-                for (int n = 0; n < NB; ++n) {
-                    const int src = jj0 + n;
-                    const int row00 = __shfl_sync(0xffffffffu, tap[pp].row00, src, LANES);
-                    const int pack = __shfl_sync(0xffffffffu, tap[pp].pack, src, LANES);
-                    fx[n] = __shfl_sync(0xffffffffu, tap[pp].dx, src, LANES);
-                    fy[n] = __shfl_sync(0xffffffffu, tap[pp].dy, src, LANES);
-                    fw[n] = __shfl_sync(0xffffffffu, wa[pp], src, LANES);
-                    const int step_y = pack & kPackDyMask;
-                    const int step_x = (pack >> kPackDxBit) & 1;
-                    const T *__restrict__ p00 = img_lane + (size_t)row00 * row_stride;
-                    const T *__restrict__ p01 = p00 + (size_t)step_x * row_stride;
-                    const T *__restrict__ p10 = p00 + (size_t)step_y * row_stride;
-                    const T *__restrict__ p11 = p10 + (size_t)step_x * row_stride;
-                    if constexpr (BORDER) {
-                        raw[n][0] = gather_row<T>(p00);
-                        raw[n][1] = gather_row<T>(p01);
-                        raw[n][2] = gather_row<T>(p10);
-                        raw[n][3] = gather_row<T>(p11);
-                    } else {
-                        // zeros padding: out-of-range corners read as 0 (kernels.py:227-231) and are not fetched
-                        const unsigned mask = (unsigned)(pack >> kPackMaskShift) & 0xFu;
-                        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-                        raw[n][0] = (mask & 1u) ? gather_row<T>(p00) : zero;
-                        raw[n][1] = (mask & 2u) ? gather_row<T>(p01) : zero;
-                        raw[n][2] = (mask & 4u) ? gather_row<T>(p10) : zero;
-                        raw[n][3] = (mask & 8u) ? gather_row<T>(p11) : zero;
-                    }
-                }
-#pragma unroll
-                for (int n = 0; n < NB; ++n) {
-                    const float wy1 = fw[n] * fy[n], wy0 = fw[n] - wy1;  // w*dy, w*(1-dy)
-                    float w[4];
-                    w[1] = wy0 * fx[n];
-                    w[0] = wy0 - w[1];
-                    w[3] = wy1 * fx[n];
-                    w[2] = wy1 - w[3];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        float v[VEC];
-                        widen_row<T, VEC>(raw[n][c], v);
-#pragma unroll
-                        for (int e = 0; e < VEC; ++e) acc[e] = fmaf(w[c], v[e], acc[e]);
-                    }
-                }
-            }
-        }
-        if (tu.live) store_vec<T, VEC>(out + (size_t)tu.u * a.D + j * VEC, acc);
-    }
-}
-
-template <typename T, int LANES, int LK>
-static cudaError_t launch_tiled_t(const KernelArgs &a, int sm_count, cudaStream_t st) {
-    constexpr int G = TiledCfg<T, LANES, LK>::G;
-    const int tiles_per_bh = (a.Q + G - 1) / G;
-    const long long total_tiles = (long long)a.B * a.H * tiles_per_bh;
-    const int warps = kTiledThreads / 32;
-    long long want = (total_tiles + warps - 1) / warps;
-    const int grid = (int)(want < sm_count ? (want < 1 ? 1 : want) : sm_count);
-    if (a.border)
-        msda_fwd_tiled_kernel<T, LANES, LK, true><<<grid, kTiledThreads, 0, st>>>(a, tiles_per_bh, total_tiles);
-    else
-        msda_fwd_tiled_kernel<T, LANES, LK, false><<<grid, kTiledThreads, 0, st>>>(a, tiles_per_bh, total_tiles);
-    return cudaGetLastError();
-}
-
-// Eligibility: L*K == 16, one pixel-row slice is LANES x 16 bytes with LANES in the instantiated set.
-cudaError_t launch_forward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st) {
-    if (a.LK != 16 || a.L > 16) return cudaErrorNotSupported;
-    if (dtype == 0) {
-        if (a.D == 32) return launch_tiled_t<float, 8, 16>(a, sm_count, st);
-        if (a.D == 64) return launch_tiled_t<float, 16, 16>(a, sm_count, st);
-    } else if (dtype == 1) {
-        if (a.D == 32) return launch_tiled_t<__half, 4, 16>(a, sm_count, st);
-        if (a.D == 64) return launch_tiled_t<__half, 8, 16>(a, sm_count, st);
-    } else if (dtype == 2) {
-        if (a.D == 32) return launch_tiled_t<__nv_bfloat16, 4, 16>(a, sm_count, st);
-        if (a.D == 64) return launch_tiled_t<__nv_bfloat16, 8, 16>(a, sm_count, st);
-    }
-    return cudaErrorNotSupported;
 }
 
 }  // namespace msda

@@ -1,0 +1,152 @@
+// msda_fwd_tiled.cu -- tuned forward kernel (see msda_tiled.cuh for the schedule).
+//
+// Per warp iteration: G = 32/LANES units.  Each lane resolves PPL = LK/LANES points, then the group walks the LK
+// points in batches of NB: 5 shuffles + 4 independent 128-bit gathers per point, 4*NB gathers in flight per lane on
+// top of whatever the compiler hoists from the next batch.
+#include "msda_common.cuh"
+#include "msda_launch.h"
+#include "msda_tiled.cuh"
+
+namespace msda {
+
+template <typename T, int LANES, int LK, bool BORDER, int NB, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+    msda_fwd_tiled_kernel(const KernelArgs a, const int tiles_per_bh, const int total_tiles) {
+    using Cfg = TiledCfg<T, LANES, LK>;
+    constexpr int VEC = Cfg::VEC, G = Cfg::G, PPL = Cfg::PPL;
+    static_assert(LANES % NB == 0, "batch must divide the group");
+
+    __shared__ Level s_lv[LK];
+    build_level_table(s_lv, a.shapes, a.L);
+
+    const T *__restrict__ img = static_cast<const T *>(a.img);
+    const T *__restrict__ pts = static_cast<const T *>(a.pts);
+    const T *__restrict__ aw = static_cast<const T *>(a.aw);
+    T *__restrict__ out = static_cast<T *>(a.out);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = THREADS >> 5;
+    const int j = lane % LANES, g = lane / LANES;
+    const bool align = a.align != 0;
+    const unsigned row_bytes = (unsigned)(a.H * a.D) * (unsigned)sizeof(T);
+
+    const int t_begin = (int)((long long)total_tiles * blockIdx.x / gridDim.x);
+    const int t_end = (int)((long long)total_tiles * (blockIdx.x + 1) / gridDim.x);
+
+    int tile = t_begin + warp;
+    if (tile >= t_end) return;
+
+    // software pipeline: sampling points / weights of the next warp tile are in flight while this one is processed
+    TileUnit tu = decode_tile(tile, tiles_per_bh, g, G, a);
+    float xy[2 * PPL], wa[PPL];
+    load_vec<T, 2 * PPL>(pts + ((size_t)tu.u * LK + j * PPL) * 2, xy);
+    load_vec<T, PPL>(aw + (size_t)tu.u * LK + j * PPL, wa);
+
+    for (; tile < t_end; tile += nwarps) {
+        const int tile_n = tile + nwarps;
+        const bool has_next = tile_n < t_end;
+        const TileUnit tu_n = decode_tile(has_next ? tile_n : tile, tiles_per_bh, g, G, a);
+        float xy_n[2 * PPL], wa_n[PPL];
+        load_vec<T, 2 * PPL>(pts + ((size_t)tu_n.u * LK + j * PPL) * 2, xy_n);
+        load_vec<T, PPL>(aw + (size_t)tu_n.u * LK + j * PPL, wa_n);
+
+        const unsigned char *__restrict__ lane_base =
+            reinterpret_cast<const unsigned char *>(img + tu.bh_off + j * VEC);
+
+        TileTap tap[PPL];
+#pragma unroll
+        for (int pp = 0; pp < PPL; ++pp)
+            tap[pp] = resolve_tap<BORDER>(xy[2 * pp], xy[2 * pp + 1], s_lv[(j * PPL + pp) / a.K], align, row_bytes);
+
+        float acc[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc[e] = 0.0f;
+
+#pragma unroll
+        for (int pp = 0; pp < PPL; ++pp) {
+#pragma unroll
+            for (int jj0 = 0; jj0 < LANES; jj0 += NB) {
+                uint4 raw[NB][4];
+                float fx[NB], fy[NB], fw[NB];
+#pragma unroll
+                for (int n = 0; n < NB; ++n) {
+                    const int src = jj0 + n;
+                    const unsigned off = __shfl_sync(0xffffffffu, tap[pp].off, src, LANES);
+                    const unsigned pack = __shfl_sync(0xffffffffu, tap[pp].pack, src, LANES);
+                    fx[n] = __shfl_sync(0xffffffffu, tap[pp].dx, src, LANES);
+                    fy[n] = __shfl_sync(0xffffffffu, tap[pp].dy, src, LANES);
+                    fw[n] = __shfl_sync(0xffffffffu, wa[pp], src, LANES);
+                    unsigned o[4];
+                    corner_offsets(off, pack, row_bytes, o);
+                    if constexpr (BORDER) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) raw[n][c] = gather_row(lane_base, o[c]);
+                    } else {
+                        // zeros padding: out-of-range corners read as 0 (kernels.py:227-231) and are not fetched
+                        const unsigned mask = (pack >> kPackMaskShift) & 0xFu;
+                        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) raw[n][c] = ((mask >> c) & 1u) ? gather_row(lane_base, o[c]) : zero;
+                    }
+                }
+#pragma unroll
+                for (int n = 0; n < NB; ++n) {
+                    const float wy1 = fw[n] * fy[n], wy0 = fw[n] - wy1;  // w*dy, w*(1-dy)
+                    float w[4];
+                    w[1] = wy0 * fx[n];
+                    w[0] = wy0 - w[1];
+                    w[3] = wy1 * fx[n];
+                    w[2] = wy1 - w[3];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        float v[VEC];
+                        widen_row<T, VEC>(raw[n][c], v);
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) acc[e] = fmaf(w[c], v[e], acc[e]);
+                    }
+                }
+            }
+        }
+        if (tu.live) store_vec<T, VEC>(out + (size_t)tu.u * a.D + j * VEC, acc);
+
+        tu = tu_n;
+#pragma unroll
+        for (int i = 0; i < 2 * PPL; ++i) xy[i] = xy_n[i];
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) wa[i] = wa_n[i];
+    }
+}
+
+template <typename T, int LANES, int LK>
+static cudaError_t launch_tiled_t(const KernelArgs &a, int sm_count, cudaStream_t st) {
+    constexpr int THREADS = 512, NB = 4;
+    constexpr int G = TiledCfg<T, LANES, LK>::G;
+    if (!tiled_offsets_fit(a, sizeof(T))) return cudaErrorNotSupported;
+    const int tiles_per_bh = (a.Q + G - 1) / G;
+    const int total_tiles = a.B * a.H * tiles_per_bh;
+    const int warps = THREADS / 32;
+    const int want = (total_tiles + warps - 1) / warps;
+    const int grid = (int)(want < sm_count ? (want < 1 ? 1 : want) : sm_count);
+    if (a.border)
+        msda_fwd_tiled_kernel<T, LANES, LK, true, NB, THREADS><<<grid, THREADS, 0, st>>>(a, tiles_per_bh, total_tiles);
+    else
+        msda_fwd_tiled_kernel<T, LANES, LK, false, NB, THREADS><<<grid, THREADS, 0, st>>>(a, tiles_per_bh, total_tiles);
+    return cudaGetLastError();
+}
+
+// Eligibility: L*K == 16, one pixel-row slice is LANES x 16 bytes with LANES in the instantiated set.
+cudaError_t launch_forward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st) {
+    if (a.LK != 16 || a.L > 16) return cudaErrorNotSupported;
+    if (dtype == 0) {
+        if (a.D == 32) return launch_tiled_t<float, 8, 16>(a, sm_count, st);
+        if (a.D == 64) return launch_tiled_t<float, 16, 16>(a, sm_count, st);
+    } else if (dtype == 1) {
+        if (a.D == 32) return launch_tiled_t<__half, 4, 16>(a, sm_count, st);
+        if (a.D == 64) return launch_tiled_t<__half, 8, 16>(a, sm_count, st);
+    } else if (dtype == 2) {
+        if (a.D == 32) return launch_tiled_t<__nv_bfloat16, 4, 16>(a, sm_count, st);
+        if (a.D == 64) return launch_tiled_t<__nv_bfloat16, 8, 16>(a, sm_count, st);
+    }
+    return cudaErrorNotSupported;
+}
+
+}  // namespace msda
