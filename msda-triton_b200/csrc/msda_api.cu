@@ -168,10 +168,16 @@ int msda_forward(void *out, const void *img, const int64_t *img_shapes, const vo
 
 size_t msda_backward_workspace_bytes(const msda_problem *prob, int flags) {
     if (validate(prob) != MSDA_OK) return 0;
-    size_t bytes = 0;
-    if ((flags & MSDA_BWD_NEED_IMG) && (prob->dtype == MSDA_DTYPE_F16 || prob->dtype == MSDA_DTYPE_BF16))
-        bytes += sizeof(float) * (size_t)prob->B * prob->Npix * prob->H * prob->D;
-    return bytes;
+    if (!(flags & MSDA_BWD_NEED_IMG) || prob->B == 0) return 0;
+    if (flags & MSDA_BWD_DETERMINISTIC) {
+        if (prob->Q == 0) return 0;
+        msda::KernelArgs a;
+        fill_args(a, prob, 1);
+        return msda::det_supported(a) ? msda::det_workspace_bytes(a) : 0;
+    }
+    if (prob->dtype == MSDA_DTYPE_F16 || prob->dtype == MSDA_DTYPE_BF16)
+        return sizeof(float) * (size_t)prob->B * prob->Npix * prob->H * prob->D;
+    return 0;
 }
 
 int msda_backward(void *grad_img, void *grad_points, void *grad_weights, const void *grad_out, const void *img,
@@ -192,12 +198,49 @@ int msda_backward(void *grad_img, void *grad_points, void *grad_weights, const v
     rc = device_info(&dev);
     if (rc != MSDA_OK) return rc;
 
+    if ((flags & MSDA_BWD_DETERMINISTIC) && need_img) {
+        // grad_points / grad_weights from the regular kernel (no atomics there), grad_img by sorted segments
+        if (need_pts || need_aw) {
+            rc = msda_backward(nullptr, grad_points, grad_weights, grad_out, img, img_shapes, sampling_points,
+                               attention_weights, prob, flags & (MSDA_BWD_NEED_POINTS | MSDA_BWD_NEED_WEIGHTS), nullptr,
+                               0, stream);
+            if (rc != MSDA_OK) return rc;
+        }
+        if (img_elems == 0) return MSDA_OK;
+        if (no_units) {
+            cudaError_t e0 = cudaMemsetAsync(grad_img, 0, img_elems * es, st);
+            return e0 == cudaSuccess ? MSDA_OK : fail_cuda(e0, "msda_backward zero-fill");
+        }
+        if (!grad_out || !img_shapes || !sampling_points || !attention_weights)
+            return fail(MSDA_ERR_NULL_POINTER, "msda_backward: NULL device pointer");
+        if (!aligned(sampling_points, 2 * es) || !aligned(img_shapes, 8))
+            return fail(MSDA_ERR_BAD_SHAPE, "msda_backward: sampling_points must be aligned to one (x,y) pair");
+        const int dvec = pick_vec(prob, {grad_out, grad_img});
+        msda::KernelArgs d;
+        fill_args(d, prob, dvec);
+        if (!msda::det_supported(d))
+            return fail(MSDA_ERR_BAD_SHAPE, "msda_backward: problem too large for the deterministic mode (needs "
+                                            "B*Q*H*L*K*4 < 2^32 and B*Npix*H < 2^32)");
+        const size_t want = msda::det_workspace_bytes(d);
+        if (!workspace || workspace_bytes < want || !aligned(workspace, 256))
+            return fail(MSDA_ERR_WORKSPACE, "msda_backward: deterministic mode needs a 256-byte aligned workspace of "
+                                            "%zu bytes, got %zu", want, workspace_bytes);
+        d.shapes = reinterpret_cast<const long long *>(img_shapes);
+        d.pts = sampling_points;
+        d.aw = attention_weights;
+        d.gout = grad_out;
+        d.gimg = grad_img;
+        cudaError_t e1 = msda::launch_backward_det(d, prob->dtype, dvec, workspace, dev.sm_count, st);
+        if (e1 != cudaSuccess) return fail_cuda(e1, "msda_backward deterministic path");
+        return MSDA_OK;
+    }
+
     // grad_img accumulates in fp32 (fp64 for f64): directly in grad_img for f32/f64, in the workspace for 16-bit.
     const bool staged = need_img && (prob->dtype == MSDA_DTYPE_F16 || prob->dtype == MSDA_DTYPE_BF16);
     void *accum = grad_img;
     size_t accum_bytes = img_elems * es;
     if (staged) {
-        const size_t want = msda_backward_workspace_bytes(prob, flags);
+        const size_t want = img_elems * sizeof(float);
         if ((!workspace && want > 0) || workspace_bytes < want)
             return fail(MSDA_ERR_WORKSPACE, "msda_backward: workspace of %zu bytes required, got %zu", want,
                         workspace_bytes);

@@ -1,0 +1,183 @@
+// msda_bwd_det.cu -- deterministic grad_img: sorted-segment reduction instead of atomics (MSDA_BWD_DETERMINISTIC).
+//
+// The reference's backward adds into grad_img with tl.atomic_add (src/msda_triton/kernels.py:549-553), so the fp32
+// summation order -- and therefore the low bits of grad_img -- changes from run to run.  This path produces
+// bit-identical grad_img on every run:
+//   1. keys   : every bilinear corner (unit, point, corner) emits key = destination row (b, pixel, h) and
+//               value = its own index; invalid (zeros-mode, out-of-range) corners get the sentinel key 0xFFFFFFFF.
+//   2. sort   : stable LSD radix sort by key (cub::DeviceRadixSort, deterministic), so inside a segment the
+//               contributions are ordered by (unit, point, corner).
+//   3. reduce : one lane group per destination row walks its segment IN THAT ORDER, recomputes the corner weight
+//               from the sampling point, and accumulates weight * grad_out[unit] in registers; the row is written
+//               once with a plain store (no zero-fill, no atomics, one rounding to the storage dtype).
+// grad_sampling_points / grad_attention_weights never needed atomics and come from the regular backward kernel.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "msda_common.cuh"
+#include "msda_launch.h"
+
+namespace msda {
+
+constexpr unsigned kDetSentinel = 0xFFFFFFFFu;
+
+template <typename T>
+__global__ void __launch_bounds__(256) det_keys_kernel(const KernelArgs a, unsigned *__restrict__ keys,
+                                                       unsigned *__restrict__ vals, const long long n_points) {
+    using CT = typename Traits<T>::CT;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    Level *s_lv = reinterpret_cast<Level *>(s_raw);
+    build_level_table(s_lv, a.shapes, a.L);
+    const T *__restrict__ pts = static_cast<const T *>(a.pts);
+    const bool border = a.border != 0, align = a.align != 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_points; i += stride) {
+        const long long u = i / a.LK;
+        const int p = (int)(i - u * a.LK);
+        const int h = (int)(u % a.H);
+        const long long b = u / ((long long)a.H * a.Q);
+        CT xy[2];
+        load_vec<T, 2>(pts + 2 * i, xy);
+        const Tap<CT> t = locate<CT>(xy[0], xy[1], s_lv[p / a.K], border, align);
+        const int step_y = t.pack & kPackDyMask;
+        const int step_x = (t.pack >> kPackDxBit) & 1;
+        const unsigned mask = (unsigned)(t.pack >> kPackMaskShift) & 0xFu;
+        const int rows[4] = {t.row00, t.row00 + step_x, t.row00 + step_y, t.row00 + step_y + step_x};
+        uint4 k4, v4;
+        unsigned *kk = reinterpret_cast<unsigned *>(&k4), *vv = reinterpret_cast<unsigned *>(&v4);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const unsigned long long key = ((unsigned long long)b * a.Npix + rows[c]) * a.H + h;
+            kk[c] = ((mask >> c) & 1u) ? (unsigned)key : kDetSentinel;
+            vv[c] = (unsigned)(4 * i + c);
+        }
+        reinterpret_cast<uint4 *>(keys)[i] = k4;
+        reinterpret_cast<uint4 *>(vals)[i] = v4;
+    }
+}
+
+// One group of `lanes` lanes per destination row; lane j owns VEC channels of each chunk.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) det_reduce_kernel(const KernelArgs a, const unsigned *__restrict__ keys,
+                                                         const unsigned *__restrict__ vals, const long long n,
+                                                         const long long n_rows) {
+    using CT = typename Traits<T>::CT;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    Level *s_lv = reinterpret_cast<Level *>(s_raw);
+    build_level_table(s_lv, a.shapes, a.L);
+    const T *__restrict__ pts = static_cast<const T *>(a.pts);
+    const T *__restrict__ aw = static_cast<const T *>(a.aw);
+    const T *__restrict__ gout = static_cast<const T *>(a.gout);
+    T *__restrict__ gimg = static_cast<T *>(a.gimg);
+    const int lanes = a.lanes;
+    const int j = threadIdx.x & (lanes - 1);
+    const int groups_per_cta = blockDim.x / lanes;
+    const bool border = a.border != 0, align = a.align != 0;
+
+    for (long long r = (long long)blockIdx.x * groups_per_cta + threadIdx.x / lanes; r < n_rows;
+         r += (long long)gridDim.x * groups_per_cta) {
+        // lower_bound(keys, r): first contribution of this row (all lanes of the group search redundantly)
+        long long lo = 0, hi = n;
+        const unsigned key = (unsigned)r;
+        while (lo < hi) {
+            const long long mid = (lo + hi) >> 1;
+            if (keys[mid] < key) lo = mid + 1; else hi = mid;
+        }
+        for (int chunk = 0; chunk < a.chunks; ++chunk) {
+            const int c0 = (chunk * lanes + j) * VEC;
+            if (c0 >= a.D) continue;
+            CT acc[VEC];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[e] = (CT)0;
+            for (long long i = lo; i < n && keys[i] == key; ++i) {
+                const unsigned v = vals[i];
+                const int c = (int)(v & 3u);
+                const long long pi = (long long)(v >> 2);         // (unit, point) index
+                const long long u = pi / a.LK;
+                const int p = (int)(pi - u * a.LK);
+                CT xy[2];
+                load_vec<T, 2>(pts + 2 * pi, xy);
+                const Tap<CT> t = locate<CT>(xy[0], xy[1], s_lv[p / a.K], border, align);
+                const CT wx = (c & 1) ? t.dx : (CT)1 - t.dx;
+                const CT wy = (c & 2) ? t.dy : (CT)1 - t.dy;
+                const CT w = Traits<T>::to_ct(aw[pi]) * (wy * wx);
+                CT go[VEC];
+                load_vec<T, VEC>(gout + (size_t)u * a.D + c0, go);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) acc[e] += go[e] * w;
+            }
+            store_vec<T, VEC>(gimg + (size_t)r * a.D + c0, acc);
+        }
+    }
+}
+
+static int grid_for(long long work_items, int per_cta, int sm_count) {
+    long long want = (work_items + per_cta - 1) / per_cta;
+    const long long cap = (long long)sm_count * 32;
+    return (int)(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
+size_t det_sort_temp_bytes(long long n) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned *)nullptr, (unsigned *)nullptr,
+                                    (const unsigned *)nullptr, (unsigned *)nullptr, n);
+    return bytes;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+size_t det_workspace_bytes(const KernelArgs &a) {
+    const long long n = a.units * a.LK * 4;
+    return 4 * align_up((size_t)n * sizeof(unsigned), 256) + align_up(det_sort_temp_bytes(n), 256);
+}
+
+bool det_supported(const KernelArgs &a) {
+    const unsigned long long n = (unsigned long long)a.units * a.LK * 4;
+    const unsigned long long rows = (unsigned long long)a.B * a.Npix * a.H;
+    return n < 0xFFFFFFFFull && rows < 0xFFFFFFFFull;
+}
+
+template <typename T>
+static cudaError_t launch_det_t(const KernelArgs &a, int vec, void *workspace, int sm_count, cudaStream_t st) {
+    const long long n_points = a.units * a.LK, n = n_points * 4;
+    const long long n_rows = (long long)a.B * a.Npix * a.H;
+    const size_t arr = align_up((size_t)n * sizeof(unsigned), 256);
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    unsigned *keys_in = reinterpret_cast<unsigned *>(ws), *keys_out = reinterpret_cast<unsigned *>(ws + arr);
+    unsigned *vals_in = reinterpret_cast<unsigned *>(ws + 2 * arr), *vals_out = reinterpret_cast<unsigned *>(ws + 3 * arr);
+    void *temp = ws + 4 * arr;
+    size_t temp_bytes = det_sort_temp_bytes(n);
+    const size_t smem = sizeof(Level) * (size_t)a.L;
+
+    det_keys_kernel<T><<<grid_for(n_points, 256, sm_count), 256, smem, st>>>(a, keys_in, vals_in, n_points);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    // keys are < B*Npix*H or the all-ones sentinel: sort on all 32 bits
+    e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, n, 0, 32, st);
+    if (e != cudaSuccess) return e;
+    const int groups_per_cta = 256 / a.lanes;
+    const int grid = grid_for(n_rows, groups_per_cta, sm_count);
+    switch (vec) {
+        case 8:
+            if constexpr (Traits<T>::kMaxVec >= 8) det_reduce_kernel<T, 8><<<grid, 256, smem, st>>>(a, keys_out, vals_out, n, n_rows);
+            break;
+        case 4:
+            if constexpr (Traits<T>::kMaxVec >= 4) det_reduce_kernel<T, 4><<<grid, 256, smem, st>>>(a, keys_out, vals_out, n, n_rows);
+            break;
+        case 2: det_reduce_kernel<T, 2><<<grid, 256, smem, st>>>(a, keys_out, vals_out, n, n_rows); break;
+        default: det_reduce_kernel<T, 1><<<grid, 256, smem, st>>>(a, keys_out, vals_out, n, n_rows); break;
+    }
+    return cudaGetLastError();
+}
+
+// a.gimg must point at the grad_img tensor in STORAGE dtype (rows are written once, no accumulation image).
+cudaError_t launch_backward_det(const KernelArgs &a, int dtype, int vec, void *workspace, int sm_count, cudaStream_t st) {
+    switch (dtype) {
+        case 0: return launch_det_t<float>(a, vec, workspace, sm_count, st);
+        case 1: return launch_det_t<__half>(a, vec, workspace, sm_count, st);
+        case 2: return launch_det_t<__nv_bfloat16>(a, vec, workspace, sm_count, st);
+        case 3: return launch_det_t<double>(a, vec, workspace, sm_count, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace msda

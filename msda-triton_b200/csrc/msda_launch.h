@@ -15,6 +15,11 @@ cudaError_t launch_backward_generic(const KernelArgs &a, int dtype, int vec, int
 cudaError_t launch_forward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st);
 cudaError_t launch_backward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st);
 
+// Deterministic grad_img (sorted-segment reduction, msda_bwd_det.cu).  a.gimg = grad_img in STORAGE dtype.
+bool det_supported(const KernelArgs &a);
+size_t det_workspace_bytes(const KernelArgs &a);
+cudaError_t launch_backward_det(const KernelArgs &a, int dtype, int vec, void *workspace, int sm_count, cudaStream_t st);
+
 // grad_img epilogue for 16-bit storage: rounds the fp32 accumulation image to T.
 cudaError_t launch_round_grad_img(void *dst, const float *src, long long n, int dtype, cudaStream_t st);
 

@@ -1,0 +1,138 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/msda_b200.h declares (no compute calls
+without a GPU), the Python surface matches the reference's names / signatures / state_dict keys, the CPU-tensor route
+agrees with the oracle, and the CUDA route refuses to run without CUDA tensors."""
+import ctypes
+import inspect
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from util import BENCH_PYRAMID, assert_close, make_inputs, to_np
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def libpath():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("msda_b200_build", ROOT / "msda-triton_b200" / "build.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.build_library()
+
+
+def declared_symbols():
+    text = (ROOT / "include" / "msda_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(msda_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_declares_the_expected_entry_points():
+    assert declared_symbols() == sorted([
+        "msda_abi_version", "msda_last_error", "msda_forward", "msda_backward_workspace_bytes", "msda_backward",
+        "msda_level_table", "msda_probe_gather", "msda_probe_scatter"])
+
+
+def test_library_exports_every_declared_symbol(libpath):
+    lib = ctypes.CDLL(str(libpath))
+    for name in declared_symbols():
+        assert hasattr(lib, name), f"{name} declared in include/msda_b200.h but not exported"
+    lib.msda_abi_version.restype = ctypes.c_int
+    assert lib.msda_abi_version() == 1
+    lib.msda_last_error.restype = ctypes.c_char_p
+    assert isinstance(lib.msda_last_error(), bytes)
+
+
+def test_argument_validation_needs_no_gpu(libpath):
+    from msda_triton import _lib
+    lib = _lib.get_lib()
+    bad = _lib.MsdaProblem(1, 10, 2, 8, 4, 1, 1, 99, 0, 0, 0)       # unknown dtype code
+    rc = lib.msda_forward(None, None, None, None, None, ctypes.byref(bad), None)
+    assert rc == -2 and b"dtype" in lib.msda_last_error()
+    bad = _lib.MsdaProblem(1, 10, 2, 8, 4, 1, 1, 0, 7, 0, 0)        # unknown padding mode
+    assert lib.msda_forward(None, None, None, None, None, ctypes.byref(bad), None) == -4
+    ok = _lib.MsdaProblem(2, 5440, 8, 32, 100, 4, 4, _lib.DTYPE_BF16, 0, 0, 0)
+    assert lib.msda_backward_workspace_bytes(ctypes.byref(ok), 7) == 2 * 5440 * 8 * 32 * 4
+    ok32 = _lib.MsdaProblem(2, 5440, 8, 32, 100, 4, 4, _lib.DTYPE_F32, 0, 0, 0)
+    assert lib.msda_backward_workspace_bytes(ctypes.byref(ok32), 7) == 0
+    assert lib.msda_backward_workspace_bytes(ctypes.byref(ok32), 7 | 8) >= 4 * 4 * (2 * 100 * 8 * 16 * 4)
+
+
+def test_public_surface_matches_reference():
+    import msda_triton
+    from msda_triton import frontend
+    assert set(msda_triton.__all__) == {"multiscale_deformable_attention", "MultiscaleDeformableAttention"}
+    assert isinstance(msda_triton.__version__, str)
+    for name in ("triton_multiscale_deformable_attention", "native_multiscale_deformable_attention",
+                 "MultiscaleDeformableAttention", "multiscale_deformable_attention"):
+        assert hasattr(frontend, name)
+    want = ["img", "img_shapes", "sampling_points", "attention_weights", "padding_mode", "align_corners"]
+    for fn in (frontend.multiscale_deformable_attention, frontend.triton_multiscale_deformable_attention,
+               frontend.native_multiscale_deformable_attention):
+        assert list(inspect.signature(fn).parameters) == want
+    ctor = list(inspect.signature(frontend.MultiscaleDeformableAttention.__init__).parameters)[1:]
+    assert ctor == ["emb_dim", "hidden_dim", "num_levels", "num_heads", "num_points", "padding_mode", "align_corners"]
+    m = frontend.MultiscaleDeformableAttention(64, 32, 3, 4, 2, "zeros", False)
+    assert sorted(m.state_dict()) == sorted(f"{p}.{w}" for p in ("img_input_proj", "query_input_proj", "query_output_proj")
+                                            for w in ("weight", "bias"))
+    assert m.query_input_proj.out_features == 4 * 3 * 2 * 3
+    with pytest.raises(ValueError):
+        frontend.MultiscaleDeformableAttention(64, 30, 3, 4, 2, "zeros", False)
+
+
+def test_cuda_route_rejects_cpu_tensors_and_bad_dtypes():
+    from msda_triton.frontend import triton_multiscale_deformable_attention as cuda_route
+    img, s, pts, aw, _ = make_inputs(1, 4, 2, 8, [(4, 4)], 2)
+    with pytest.raises(ValueError, match="gpu"):
+        cuda_route(img, s, pts, aw, "zeros", False)
+    with pytest.raises(ValueError, match="Dtype"):
+        cuda_route(img.to(torch.int32), s, pts, aw, "zeros", False)
+
+
+@pytest.mark.parametrize("pm", ["zeros", "border"])
+@pytest.mark.parametrize("ac", [False, True])
+def test_cpu_tensor_route_matches_oracle(pm, ac):
+    """CPU tensors take the torch route the reference documents for device='cpu' (README.md:132)."""
+    import msda_triton
+    from oracle import msda_oracle
+    img, s, pts, aw, go = make_inputs(2, 40, 4, 16, [(9, 7), (5, 4), (2, 3)], 3, dtype=torch.float64, seed=3, points="wide")
+    a, b, c = (t.clone().requires_grad_(True) for t in (img, pts, aw))
+    out = msda_triton.multiscale_deformable_attention(a, s, b, c, pm, ac)
+    out.backward(go)
+    ref_out = msda_oracle.forward(img, s, pts, aw, pm, ac)
+    rgi, rgp, rga = msda_oracle.backward(go, img, s, pts, aw, pm, ac)
+    assert_close(to_np(out), ref_out, 1e-9, 1e-10, "out")
+    assert_close(to_np(a.grad), rgi, 1e-9, 1e-10, "grad_img")
+    assert_close(to_np(c.grad), rga, 1e-9, 1e-10, "grad_weights")
+    assert_close(to_np(b.grad), rgp, 1e-8, 1e-9 * np.abs(rgp).max(), "grad_points")
+
+
+@pytest.mark.parametrize("coords", [2, 4])
+def test_module_on_cpu(coords):
+    """Mirrors the reference's only GPU-less test (tests/test_msda.py:154-168): D = 4, K = 8, randn reference points."""
+    from msda_triton import MultiscaleDeformableAttention
+    torch.manual_seed(0)
+    channels, heads, levels, points = 256, 8, 4, 8
+    npix = sum(h * w for h, w in BENCH_PYRAMID)
+    img = torch.randn(2, npix, channels)
+    queries = torch.randn(2, 50, channels)
+    ref_pts = torch.randn(2, 50, coords)
+    module = MultiscaleDeformableAttention(channels, channels // heads, levels, heads, points, "border", True)
+    out = module(img, torch.tensor(BENCH_PYRAMID), queries, ref_pts)
+    assert out.shape == (2, 50, channels) and torch.isfinite(out).all()
+    with pytest.raises(ValueError):
+        module(img, torch.tensor(BENCH_PYRAMID), queries, torch.randn(2, 50, 3))
+
+
+def test_grid_sample_port_matches_oracle():
+    """The CPU-baseline port (oracle/grid_sample_port.py) and the C oracle are two independent restatements."""
+    from oracle import grid_sample_port, msda_oracle
+    img, s, pts, aw, go = make_inputs(2, 30, 3, 8, [(6, 7), (3, 4)], 4, dtype=torch.float64, seed=8, points="wide")
+    out, gi, gp, ga = grid_sample_port.forward_backward(img, s, pts, aw, go, "zeros", False)
+    assert_close(to_np(out), msda_oracle.forward(img, s, pts, aw, "zeros", False), 1e-9, 1e-10, "out")
+    rgi, rgp, rga = msda_oracle.backward(go, img, s, pts, aw, "zeros", False)
+    assert_close(to_np(gi), rgi, 1e-9, 1e-10, "grad_img")
+    assert_close(to_np(ga), rga, 1e-9, 1e-10, "grad_weights")

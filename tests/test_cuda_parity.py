@@ -270,3 +270,35 @@ def test_bad_arguments_raise(K):
         K.b200_multi_scale_deformable_attention_fwd(img.cuda(), s.cuda(), pts.cuda()[:, :, :1], aw.cuda(), "zeros", False)
     with pytest.raises(ValueError):
         K.b200_multi_scale_deformable_attention_fwd(img.cuda().half(), s.cuda(), pts.cuda(), aw.cuda(), "zeros", False)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# deterministic (sorted-segment) grad_img
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,dtype", [("readme_c1_wide", torch.float32), ("ref_fixture_k3", torch.float32),
+                                        ("odd_everything", torch.float64), ("ref_module_d4_k8", torch.float32),
+                                        ("d64", torch.bfloat16)])
+@pytest.mark.parametrize("pm,ac", [("zeros", False), ("border", True)])
+def test_deterministic_mode(K, oracle, name, dtype, pm, ac):
+    B, Q, H, D, shapes, Kp, points, weights = CASES[name]
+    img, s, pts, aw, go = make_inputs(B, Q, H, D, shapes, Kp, dtype=dtype, seed=13, points=points, weights=weights)
+    runs = [run_cuda(K, img, s, pts, aw, go, pm, ac, deterministic=True) for _ in range(3)]
+    for r in runs[1:]:
+        for a, b in zip(runs[0][1:], r[1:]):
+            assert torch.equal(a, b), "deterministic mode must be bit-reproducible"
+    ref = (oracle.forward(img, s, pts, aw, pm, ac),) + oracle.backward(go, img, s, pts, aw, pm, ac)
+    if dtype in (torch.float32, torch.float64):
+        check_against(runs[0], ref, dtype, f"deterministic {name}")
+    else:
+        eps = _bounds(dtype)
+        assert_close(to_np(runs[0][1]), ref[1], eps, eps * 1e-2 * np.abs(ref[1]).max(), "deterministic bf16 grad_img")
+
+
+def test_deterministic_full_size_bitwise(K):
+    B, Q, H, D, shapes, Kp = FULL["bench_q10k"]
+    img, s, pts, aw, go = make_inputs(B, Q, H, D, shapes, Kp, seed=5)
+    a = run_cuda(K, img, s, pts, aw, go, "border", True, deterministic=True, needs=(True, False, False))[1]
+    b = run_cuda(K, img, s, pts, aw, go, "border", True, deterministic=True, needs=(True, False, False))[1]
+    c = run_cuda(K, img, s, pts, aw, go, "border", True, deterministic=False, needs=(True, False, False))[1]
+    assert torch.equal(a, b)
+    assert_close(to_np(a), to_np(c), 1e-4, 1e-5 * float(c.abs().max()), "deterministic vs atomic")
