@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(THREADS, 1)
             for (int jj0 = 0; jj0 < LANES; jj0 += NB) {
                 uint4 raw[NB][4];
                 float fx[NB], fy[NB], fw[NB];
+                unsigned msk[NB];
 #pragma unroll
                 for (int n = 0; n < NB; ++n) {
                     const int src = jj0 + n;
@@ -75,18 +76,14 @@ __global__ void __launch_bounds__(THREADS, 1)
                     fx[n] = __shfl_sync(0xffffffffu, tap[pp].dx, src, LANES);
                     fy[n] = __shfl_sync(0xffffffffu, tap[pp].dy, src, LANES);
                     fw[n] = __shfl_sync(0xffffffffu, wa[pp], src, LANES);
+                    msk[n] = (pack >> kPackMaskShift) & 0xFu;
                     unsigned o[4];
                     corner_offsets(off, pack, row_bytes, o);
-                    if constexpr (BORDER) {
+                    // corner rows are clamped into the level, so all four gathers are always in range; zeros padding
+                    // (kernels.py:227-231: out-of-range corners read as 0) is applied when the values are consumed,
+                    // which keeps the 4*NB loads independent and in flight together
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) raw[n][c] = gather_row(lane_base, o[c]);
-                    } else {
-                        // zeros padding: out-of-range corners read as 0 (kernels.py:227-231) and are not fetched
-                        const unsigned mask = (pack >> kPackMaskShift) & 0xFu;
-                        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) raw[n][c] = ((mask >> c) & 1u) ? gather_row(lane_base, o[c]) : zero;
-                    }
+                    for (int c = 0; c < 4; ++c) raw[n][c] = gather_row(lane_base, o[c]);
                 }
 #pragma unroll
                 for (int n = 0; n < NB; ++n) {
@@ -100,8 +97,10 @@ __global__ void __launch_bounds__(THREADS, 1)
                     for (int c = 0; c < 4; ++c) {
                         float v[VEC];
                         widen_row<T, VEC>(raw[n][c], v);
+                        if (BORDER || ((msk[n] >> c) & 1u)) {
 #pragma unroll
-                        for (int e = 0; e < VEC; ++e) acc[e] = fmaf(w[c], v[e], acc[e]);
+                            for (int e = 0; e < VEC; ++e) acc[e] = fmaf(w[c], v[e], acc[e]);
+                        }
                     }
                 }
             }

@@ -302,3 +302,17 @@ def test_deterministic_full_size_bitwise(K):
     c = run_cuda(K, img, s, pts, aw, go, "border", True, deterministic=False, needs=(True, False, False))[1]
     assert torch.equal(a, b)
     assert_close(to_np(a), to_np(c), 1e-4, 1e-5 * float(c.abs().max()), "deterministic vs atomic")
+
+
+@pytest.mark.parametrize("variant", ["1", "2", "3"])
+@pytest.mark.parametrize("pm,ac", [("zeros", False), ("border", True)])
+def test_binned_backward_variants(K, oracle, variant, pm, ac):
+    """The opt-in binned backward (in-CTA segmented reduction of the coarse levels) must match the oracle too."""
+    img, s, pts, aw, go = make_inputs(2, 700, 8, 32, BENCH_PYRAMID, 4, seed=17, points="wide", weights="softmax_lk")
+    os.environ["MSDA_B200_BWD_BINNED"] = variant
+    try:
+        test = run_cuda(K, img, s, pts, aw, go, pm, ac)
+    finally:
+        os.environ.pop("MSDA_B200_BWD_BINNED")
+    ref = (oracle.forward(img, s, pts, aw, pm, ac),) + oracle.backward(go, img, s, pts, aw, pm, ac)
+    check_against(test, ref, torch.float32, f"binned variant {variant}")
