@@ -39,6 +39,7 @@ WORKLOADS = {
     "bench_q10k_border": (4, 10000, 8, 32, BENCH_PYRAMID, 4, "border", True),
     "bench_q10k_zeros": (4, 10000, 8, 32, BENCH_PYRAMID, 4, "zeros", False),
     "detr_encoder_zeros": (2, 22223, 8, 32, DETR_PYRAMID, 4, "zeros", False),
+    "train_b64_encoder_zeros": (64, 22223, 8, 32, DETR_PYRAMID, 4, "zeros", False),   # BASELINE configs[4], whole batch
 }
 HEADLINE = "bench_q10k_border"
 METRIC = "MSDA fwd+bwd throughput, 10k-query benchmark shape (fp32)"
@@ -273,10 +274,15 @@ def time_workload(name, steps, warmup, K, flush, dist_sync=None, clock_index=Non
     return res
 
 
-def time_e2e(name, steps, warmup, dist_sync=None):
-    """Public API, host buffers: H2D of the step's inputs from pinned memory, fwd + autograd bwd, D2H of out and the
-    three gradients -- all inside the timed region."""
+def time_e2e(name, steps, warmup, dist_sync=None, pipelined=True):
+    """End to end with HOST buffers: every step copies its inputs (img, points, weights, grad_out) from pinned host
+    memory to the device, runs forward + backward, and copies out + the three gradients back to pinned host memory --
+    all inside the timed region.
+    pipelined=True : the package's host-buffer entry point msda_triton.host.HostMsda (per-image chunks, H2D / kernels /
+                     D2H overlapped on three streams).
+    pipelined=False: plain user code around the autograd op (tensor.to('cuda') ... out.backward(go) ... .cpu())."""
     import msda_triton
+    from msda_triton.host import HostMsda
     B, Q, H, D, pyr, Kp, pm, ac = WORKLOADS[name]
     host, shapes = make_inputs(name, seed=0, pin=True)
     shapes_dev = shapes.cuda()
@@ -286,8 +292,12 @@ def time_e2e(name, steps, warmup, dist_sync=None):
     h_ga = torch.empty_like(host["aw"]).pin_memory()
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     d2h = sum(v.numel() * v.element_size() for v in (h_out, h_gi, h_gp, h_ga))
+    pipe = HostMsda(B, host["img"].shape[1], H, D, Q, len(pyr), Kp) if pipelined else None
 
     def one_step():
+        if pipelined:
+            pipe.run(host["img"], shapes_dev, host["pts"], host["aw"], pm, ac, h_out, host["go"], h_gi, h_gp, h_ga)
+            return
         img = host["img"].to("cuda", non_blocking=True).requires_grad_(True)
         pts = host["pts"].to("cuda", non_blocking=True).requires_grad_(True)
         aw = host["aw"].to("cuda", non_blocking=True).requires_grad_(True)
@@ -313,6 +323,56 @@ def time_e2e(name, steps, warmup, dist_sync=None):
     if dist_sync:
         dist_sync()
     return e0.elapsed_time(e1) / steps, h2d, d2h
+
+
+def time_module(flush, steps=20):
+    """BASELINE configs[3]: Grounding-DINO decoder through the nn.Module -- B=8, Q=900, emb=hidden=256, H=8, L=4, K=4,
+    border / align_corners=True, bf16 parameters and inputs; fwd+bwd of the whole module and of the op inside it."""
+    from msda_triton import MultiscaleDeformableAttention, kernels as K
+    B, Q, emb, H, L, Kp = 8, 900, 256, 8, 4, 4
+    res = {}
+    for pname, pyr in (("pyramid_5440", BENCH_PYRAMID), ("pyramid_22223", DETR_PYRAMID)):
+        npix = sum(h * w for h, w in pyr)
+        g = torch.Generator().manual_seed(0)
+        dt = torch.bfloat16
+        img = torch.randn(B, npix, emb, generator=g).to("cuda", dt).requires_grad_(True)
+        queries = torch.randn(B, Q, emb, generator=g).to("cuda", dt).requires_grad_(True)
+        ref = torch.rand(B, Q, 2, generator=g).to("cuda", dt)
+        shapes = torch.tensor(pyr, device="cuda")
+        mod = MultiscaleDeformableAttention(emb, emb, L, H, Kp, "border", True).to("cuda", dt)
+        gout = torch.rand(B, Q, emb, generator=g).to("cuda", dt)
+
+        def step():
+            out = mod(img, shapes, queries, ref)
+            out.backward(gout)
+
+        # the op alone on module-like operands
+        v = torch.randn(B, npix, H, emb // H, generator=g).to("cuda", dt)
+        pts = torch.rand(B, Q, H, L, Kp, 2, generator=g).to("cuda", dt)
+        aw = torch.softmax(torch.randn(B, Q, H, L * Kp, generator=g), -1).reshape(B, Q, H, L, Kp).to("cuda", dt)
+        go = torch.rand(B, Q, H, emb // H, generator=g).to("cuda", dt)
+
+        def op_step():
+            K.b200_multi_scale_deformable_attention_fwd(v, shapes, pts, aw, "border", True)
+            K.b200_multi_scale_deformable_attention_bwd(go, v, shapes, pts, aw, "border", True)
+
+        out = {}
+        for label, fn in (("module_fwd_bwd_ms", step), ("op_fwd_bwd_ms", op_step)):
+            for _ in range(3):
+                fn()
+            ts = []
+            for _ in range(steps):
+                flush.fill_(1.0)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            ts.sort()
+            out[label] = ts[len(ts) // 2]
+        res[pname] = out
+    return res
 
 
 def l2_probe(K_lib):
@@ -369,13 +429,15 @@ def run_ours(args):
 
     head = time_workload(HEADLINE, args.steps, args.warmup, K, flush, dist_sync=sync,
                          clock_index=physical_gpu_index(local))
-    e2e_ms, h2d, d2h = time_e2e(HEADLINE, max(3, min(args.steps, 20)), 3, dist_sync=sync)
+    e2e_ms, h2d, d2h = time_e2e(HEADLINE, max(3, min(args.steps, 20)), 3, dist_sync=sync, pipelined=True)
+    e2e_plain_ms, _, _ = time_e2e(HEADLINE, max(3, min(args.steps, 10)), 3, dist_sync=sync, pipelined=False)
 
     # max over ranks of the device time
-    tmax = torch.tensor([head["step_ms"], head["fwd_ms"], head["bwd_ms"], e2e_ms], device="cuda", dtype=torch.float64)
+    tmax = torch.tensor([head["step_ms"], head["fwd_ms"], head["bwd_ms"], e2e_ms, e2e_plain_ms], device="cuda",
+                        dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    step_ms, fwd_ms, bwd_ms, e2e_ms = tmax.tolist()
+    step_ms, fwd_ms, bwd_ms, e2e_ms, e2e_plain_ms = tmax.tolist()
 
     extra = {}
     cpu = None
@@ -406,12 +468,17 @@ def run_ours(args):
             for name in WORKLOADS:
                 if name == HEADLINE:
                     continue
-                r = time_workload(name, max(5, args.steps // 4), 3, K, flush)
+                big = WORKLOADS[name][0] >= 32
+                r = time_workload(name, 5 if big else max(5, args.steps // 4), 3, K, flush)
                 bmn = byte_model(name, r["unique_rows"])
                 extra[name] = {"fwd_ms": r["fwd_ms"], "bwd_ms": r["bwd_ms"], "fwd_bwd_ms": r["step_ms"],
                                "fwd_hbm_frac": bmn["fwd"] / (r["fwd_ms"] * 1e-3) / 1e9 / peak,
                                "bwd_hbm_frac": bmn["bwd"] / (r["bwd_ms"] * 1e-3) / 1e9 / peak,
                                "fwd_gather_gbs": bmn["gather"] / (r["fwd_ms"] * 1e-3) / 1e9}
+            try:
+                extra["gdino_decoder_module_bf16"] = time_module(flush)
+            except Exception as ex:  # noqa: BLE001
+                extra["gdino_decoder_module_bf16"] = {"error": str(ex)}
             qps, ms_img, threads, sample = cpu_route_sample(HEADLINE, reps=10, warm=1)
             cpu = {"value": qps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                    "ms_per_image": ms_img}
@@ -426,7 +493,10 @@ def run_ours(args):
             "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
             "clocks": head["clocks"],
             "e2e": {"value": world * B * Q / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "msda_triton.host.HostMsda.run (pinned host buffers; per-image H2D/kernels/D2H overlap)",
+                    "autograd_unpipelined": {"value": world * B * Q / (e2e_plain_ms * 1e-3),
+                                             "ms_per_step": e2e_plain_ms}},
             "gpu_launches": 2 * args.steps,
             "roofline": roofline,
             "cpu_baseline": cpu,

@@ -1,0 +1,83 @@
+"""Host-buffer entry point: MSDA forward (+ backward) on PINNED HOST tensors with the host<->device copies pipelined
+against the kernels.
+
+The reference has no equivalent (its tensors are expected on the device already); this is the end-to-end path
+``bench.py`` reports as ``e2e``: the batch is cut into per-image chunks and three CUDA streams overlap
+
+    H2D(chunk i+1)   ||   kernels(chunk i)   ||   D2H(chunk i-1)
+
+so a step costs about max(H2D, D2H) + one chunk of compute instead of H2D + compute + D2H (PCIe is full duplex).
+Chunks are whole images because ``grad_img`` couples all queries of one image.  Device staging buffers are allocated
+once per :class:`HostMsda` and reused.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import kernels
+
+
+class HostMsda:
+    def __init__(self, batch: int, num_pixels: int, heads: int, channels: int, queries: int, levels: int, points: int,
+                 dtype: torch.dtype = torch.float32, device: Optional[torch.device] = None, backward: bool = True):
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        d = dict(dtype=dtype, device=self.device)
+        self.img = torch.empty((batch, num_pixels, heads, channels), **d)
+        self.pts = torch.empty((batch, queries, heads, levels, points, 2), **d)
+        self.aw = torch.empty((batch, queries, heads, levels, points), **d)
+        self.go = torch.empty((batch, queries, heads, channels), **d) if backward else None
+        self.batch = batch
+        self.backward = backward
+        self.h2d = torch.cuda.Stream(self.device)
+        self.d2h = torch.cuda.Stream(self.device)
+
+    @staticmethod
+    def _check_pinned(*tensors):
+        for t in tensors:
+            if t is not None and not (t.device.type == "cpu" and t.is_pinned() and t.is_contiguous()):
+                raise ValueError("HostMsda expects contiguous pinned host tensors (torch.Tensor.pin_memory())")
+
+    def run(self, img, img_shapes_dev, sampling_points, attention_weights, padding_mode, align_corners,
+            out, out_grad=None, img_grad=None, sampling_points_grad=None, attention_weights_grad=None,
+            deterministic: Optional[bool] = None):
+        """All tensor arguments except ``img_shapes_dev`` (int64 [L,2] on the device) are pinned host tensors;
+        ``out`` / ``*_grad`` are filled in place.  Returns after the last D2H copy has been ENQUEUED; the caller's
+        current stream is made to wait for it (``torch.cuda.current_stream().synchronize()`` to read the results)."""
+        do_bwd = out_grad is not None
+        if do_bwd and not self.backward:
+            raise ValueError("this HostMsda was created with backward=False")
+        self._check_pinned(img, sampling_points, attention_weights, out, out_grad, img_grad, sampling_points_grad,
+                           attention_weights_grad)
+        cur = torch.cuda.current_stream(self.device)
+        self.h2d.wait_stream(cur)     # staging buffers may still be read by earlier work on the caller's stream
+        self.d2h.wait_stream(cur)
+        needs = (img_grad is not None, sampling_points_grad is not None, attention_weights_grad is not None)
+        for b in range(self.batch):
+            sl = slice(b, b + 1)
+            with torch.cuda.stream(self.h2d):
+                self.img[sl].copy_(img[sl], non_blocking=True)
+                self.pts[sl].copy_(sampling_points[sl], non_blocking=True)
+                self.aw[sl].copy_(attention_weights[sl], non_blocking=True)
+                if do_bwd:
+                    self.go[sl].copy_(out_grad[sl], non_blocking=True)
+                ready = self.h2d.record_event()
+            cur.wait_event(ready)
+            o = kernels.b200_multi_scale_deformable_attention_fwd(
+                self.img[sl], img_shapes_dev, self.pts[sl], self.aw[sl], padding_mode, align_corners)
+            grads = (None, None, None)
+            if do_bwd and any(needs):
+                grads = kernels.b200_multi_scale_deformable_attention_bwd(
+                    self.go[sl], self.img[sl], img_shapes_dev, self.pts[sl], self.aw[sl], padding_mode, align_corners,
+                    needs=needs, deterministic=deterministic)
+            done = cur.record_event()
+            self.d2h.wait_event(done)
+            with torch.cuda.stream(self.d2h):
+                for dst, src in ((out, o), (img_grad, grads[0]), (sampling_points_grad, grads[1]),
+                                 (attention_weights_grad, grads[2])):
+                    if dst is not None and src is not None:
+                        dst[sl].copy_(src, non_blocking=True)
+                        src.record_stream(self.d2h)
+        cur.wait_stream(self.d2h)
+        return out

@@ -127,3 +127,24 @@ def test_cuda_graph_capture():
     assert torch.equal(out, eager_out)
     for a, b in zip(g, eager_g):
         assert torch.equal(a, b)
+
+
+def test_host_pipeline_matches_device_path():
+    """msda_triton.host.HostMsda (pinned host buffers, chunked H2D / kernels / D2H overlap) == plain device calls."""
+    from msda_triton import kernels as K
+    from msda_triton.host import HostMsda
+    img, s, pts, aw, go = make_inputs(3, 500, 8, 32, BENCH_PYRAMID, 4, seed=19, points="wide")
+    pin = [t.pin_memory() for t in (img, pts, aw, go)]
+    h_out = torch.empty(3, 500, 8, 32).pin_memory()
+    h_gi, h_gp, h_ga = (torch.empty_like(t).pin_memory() for t in (img, pts, aw))
+    pipe = HostMsda(3, img.shape[1], 8, 32, 500, 4, 4)
+    for _ in range(2):
+        pipe.run(pin[0], s.cuda(), pin[1], pin[2], "zeros", False, h_out, pin[3], h_gi, h_gp, h_ga, deterministic=True)
+        torch.cuda.synchronize()
+    d = [t.cuda() for t in (img, s, pts, aw, go)]
+    out = K.b200_multi_scale_deformable_attention_fwd(d[0], d[1], d[2], d[3], "zeros", False)
+    gi, gp, ga = K.b200_multi_scale_deformable_attention_bwd(d[4], d[0], d[1], d[2], d[3], "zeros", False, deterministic=True)
+    assert torch.equal(h_out, out.cpu()) and torch.equal(h_gp, gp.cpu()) and torch.equal(h_ga, ga.cpu())
+    assert torch.equal(h_gi, gi.cpu())
+    with pytest.raises(ValueError):
+        pipe.run(img, s.cuda(), pin[1], pin[2], "zeros", False, h_out)      # unpinned input
