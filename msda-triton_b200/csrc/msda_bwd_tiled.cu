@@ -16,6 +16,7 @@
 namespace msda {
 
 constexpr int kNeedImg = 1, kNeedPts = 2, kNeedAw = 4;
+constexpr size_t kBwdL2Budget = 48u << 20;  // img + grad_img bytes of one wave of (b,h) slices
 
 template <int N, int STEP> __device__ __forceinline__ void transpose_reduce(float (&part)[N], const int j) {
     // lanes with bit STEP clear keep the lower half, their partners (j ^ STEP) the upper half
@@ -35,7 +36,7 @@ template <int N, int STEP> __device__ __forceinline__ void transpose_reduce(floa
 
 template <typename T, int LANES, int LK, bool BORDER, int NB, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
-    msda_bwd_tiled_kernel(const KernelArgs a, const int tiles_per_bh, const int total_tiles) {
+    msda_bwd_tiled_kernel(const KernelArgs a, const WaveSchedule ws) {
     using Cfg = TiledCfg<T, LANES, LK>;
     constexpr int VEC = Cfg::VEC, G = Cfg::G, PPL = Cfg::PPL;
     static_assert(LANES % NB == 0, "batch must divide the group");
@@ -59,26 +60,28 @@ __global__ void __launch_bounds__(THREADS, 1)
     const unsigned row_bytes = (unsigned)(a.H * a.D) * (unsigned)sizeof(T);
     constexpr unsigned kAccScale = sizeof(float) * VEC / 16;  // accumulation row bytes / storage row bytes
 
-    const int t_begin = (int)((long long)total_tiles * blockIdx.x / gridDim.x);
-    const int t_end = (int)((long long)total_tiles * (blockIdx.x + 1) / gridDim.x);
+    const int tiles_per_bh = ws.tiles_per_bh;
+    for (int wave = 0; wave < ws.waves; ++wave) {
+    int t_begin, t_end;
+    wave_range(ws, wave, blockIdx.x, gridDim.x, t_begin, t_end);
 
     int tile = t_begin + warp;
-    if (tile >= t_end) return;
+    if (tile >= t_end) continue;
 
     TileUnit tu = decode_tile(tile, tiles_per_bh, g, G, a);
     float xy[2 * PPL], wa[PPL], go[VEC];
-    load_vec<T, 2 * PPL>(pts + ((size_t)tu.u * LK + j * PPL) * 2, xy);
-    load_vec<T, PPL>(aw + (size_t)tu.u * LK + j * PPL, wa);
-    load_vec<T, VEC>(gout + (size_t)tu.u * a.D + j * VEC, go);
+    load_vec_stream<T, 2 * PPL>(pts + ((size_t)tu.u * LK + j * PPL) * 2, xy);
+    load_vec_stream<T, PPL>(aw + (size_t)tu.u * LK + j * PPL, wa);
+    load_vec_stream<T, VEC>(gout + (size_t)tu.u * a.D + j * VEC, go);
 
     for (; tile < t_end; tile += nwarps) {
         const int tile_n = tile + nwarps;
         const bool has_next = tile_n < t_end;
         const TileUnit tu_n = decode_tile(has_next ? tile_n : tile, tiles_per_bh, g, G, a);
         float xy_n[2 * PPL], wa_n[PPL], go_n[VEC];
-        load_vec<T, 2 * PPL>(pts + ((size_t)tu_n.u * LK + j * PPL) * 2, xy_n);
-        load_vec<T, PPL>(aw + (size_t)tu_n.u * LK + j * PPL, wa_n);
-        load_vec<T, VEC>(gout + (size_t)tu_n.u * a.D + j * VEC, go_n);
+        load_vec_stream<T, 2 * PPL>(pts + ((size_t)tu_n.u * LK + j * PPL) * 2, xy_n);
+        load_vec_stream<T, PPL>(aw + (size_t)tu_n.u * LK + j * PPL, wa_n);
+        load_vec_stream<T, VEC>(gout + (size_t)tu_n.u * a.D + j * VEC, go_n);
 
         const unsigned char *__restrict__ lane_base =
             reinterpret_cast<const unsigned char *>(img + tu.bh_off + j * VEC);
@@ -163,7 +166,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                 float gw[PPL];
 #pragma unroll
                 for (int pp = 0; pp < PPL; ++pp) gw[pp] = part[3 * pp + 0];
-                store_vec<T, PPL>(gaw + (size_t)tu.u * LK + j * PPL, gw);
+                store_vec_stream<T, PPL>(gaw + (size_t)tu.u * LK + j * PPL, gw);
             }
             if (need_pts) {
                 float gp[2 * PPL];
@@ -172,7 +175,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                     gp[2 * pp + 0] = part[3 * pp + 1] * (wa[pp] * sx[pp]);
                     gp[2 * pp + 1] = part[3 * pp + 2] * (wa[pp] * sy[pp]);
                 }
-                store_vec<T, 2 * PPL>(gpts + ((size_t)tu.u * LK + j * PPL) * 2, gp);
+                store_vec_stream<T, 2 * PPL>(gpts + ((size_t)tu.u * LK + j * PPL) * 2, gp);
             }
         }
 
@@ -184,6 +187,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll
         for (int i = 0; i < VEC; ++i) go[i] = go_n[i];
     }
+    }  // waves
 }
 
 
@@ -278,9 +282,9 @@ __global__ void __launch_bounds__(THREADS, 1)
     int q_local;
     TileUnit tu = decode(st_begin, 0, q_local);
     float xy[2 * PPL], wa[PPL], go[VEC];
-    load_vec<T, 2 * PPL>(pts + ((size_t)tu.u * LK + j * PPL) * 2, xy);
-    load_vec<T, PPL>(aw + (size_t)tu.u * LK + j * PPL, wa);
-    load_vec<T, VEC>(gout + (size_t)tu.u * a.D + j * VEC, go);
+    load_vec_stream<T, 2 * PPL>(pts + ((size_t)tu.u * LK + j * PPL) * 2, xy);
+    load_vec_stream<T, PPL>(aw + (size_t)tu.u * LK + j * PPL, wa);
+    load_vec_stream<T, VEC>(gout + (size_t)tu.u * a.D + j * VEC, go);
 
     for (int st = st_begin; st < st_end; ++st) {
         size_t st_bh_off = 0;
@@ -293,9 +297,9 @@ __global__ void __launch_bounds__(THREADS, 1)
             int q_local_n;
             const TileUnit tu_n = decode(st_n, r_n, q_local_n);
             float xy_n[2 * PPL], wa_n[PPL], go_n[VEC];
-            load_vec<T, 2 * PPL>(pts + ((size_t)tu_n.u * LK + j * PPL) * 2, xy_n);
-            load_vec<T, PPL>(aw + (size_t)tu_n.u * LK + j * PPL, wa_n);
-            load_vec<T, VEC>(gout + (size_t)tu_n.u * a.D + j * VEC, go_n);
+            load_vec_stream<T, 2 * PPL>(pts + ((size_t)tu_n.u * LK + j * PPL) * 2, xy_n);
+            load_vec_stream<T, PPL>(aw + (size_t)tu_n.u * LK + j * PPL, wa_n);
+            load_vec_stream<T, VEC>(gout + (size_t)tu_n.u * a.D + j * VEC, go_n);
 
             st_bh_off = tu.bh_off;
             const unsigned char *__restrict__ lane_base =
@@ -409,7 +413,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                     float gw[PPL];
 #pragma unroll
                     for (int pp = 0; pp < PPL; ++pp) gw[pp] = part[3 * pp + 0];
-                    store_vec<T, PPL>(gaw + (size_t)tu.u * LK + j * PPL, gw);
+                    store_vec_stream<T, PPL>(gaw + (size_t)tu.u * LK + j * PPL, gw);
                 }
                 if (need_pts) {
                     float gp[2 * PPL];
@@ -418,7 +422,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                         gp[2 * pp + 0] = part[3 * pp + 1] * (wa[pp] * sx[pp]);
                         gp[2 * pp + 1] = part[3 * pp + 2] * (wa[pp] * sy[pp]);
                     }
-                    store_vec<T, 2 * PPL>(gpts + ((size_t)tu.u * LK + j * PPL) * 2, gp);
+                    store_vec_stream<T, 2 * PPL>(gpts + ((size_t)tu.u * LK + j * PPL) * 2, gp);
                 }
             }
 
@@ -491,10 +495,13 @@ static cudaError_t launch_tiled_t(const KernelArgs &a, int sm_count, cudaStream_
     const int warps = THREADS / 32;
     const int want = (total_tiles + warps - 1) / warps;
     const int grid = (int)(want < sm_count ? (want < 1 ? 1 : want) : sm_count);
+    // one wave keeps its pyramid slices AND (when grad_img is produced) the fp32 grad_img slices in L2
+    const size_t per_slice_factor = (a.flags & kNeedImg) ? sizeof(T) + sizeof(float) : sizeof(T);
+    const WaveSchedule ws = make_wave_schedule(a, tiles_per_bh, per_slice_factor, kBwdL2Budget);
     if (a.border)
-        msda_bwd_tiled_kernel<T, LANES, LK, true, NB, THREADS><<<grid, THREADS, 0, st>>>(a, tiles_per_bh, total_tiles);
+        msda_bwd_tiled_kernel<T, LANES, LK, true, NB, THREADS><<<grid, THREADS, 0, st>>>(a, ws);
     else
-        msda_bwd_tiled_kernel<T, LANES, LK, false, NB, THREADS><<<grid, THREADS, 0, st>>>(a, tiles_per_bh, total_tiles);
+        msda_bwd_tiled_kernel<T, LANES, LK, false, NB, THREADS><<<grid, THREADS, 0, st>>>(a, ws);
     return cudaGetLastError();
 }
 

@@ -110,6 +110,39 @@ __device__ __forceinline__ void store_vec(T *__restrict__ p, const typename Trai
     *reinterpret_cast<Pack<T, N> *>(p) = raw;
 }
 
+// Streaming ("cache streaming", evict-first) variants for operands that are touched exactly once per launch --
+// sampling points, attention weights, grad_out, out, grad_points, grad_weights -- so they neither displace the
+// pyramid rows in L1 nor, for large batches, in L2 (ld.global.cs / st.global.cs).
+template <int BYTES> struct RawWord;
+template <> struct RawWord<2> { using type = unsigned short; };
+template <> struct RawWord<4> { using type = unsigned; };
+template <> struct RawWord<8> { using type = uint2; };
+template <> struct RawWord<16> { using type = uint4; };
+
+template <typename T, int N>
+__device__ __forceinline__ void load_vec_stream(const T *__restrict__ p, typename Traits<T>::CT (&dst)[N]) {
+    using W = typename RawWord<sizeof(T) * N>::type;
+    union {
+        W w;
+        Pack<T, N> pack;
+    } u;
+    u.w = __ldcs(reinterpret_cast<const W *>(p));
+#pragma unroll
+    for (int i = 0; i < N; ++i) dst[i] = Traits<T>::to_ct(u.pack.v[i]);
+}
+
+template <typename T, int N>
+__device__ __forceinline__ void store_vec_stream(T *__restrict__ p, const typename Traits<T>::CT (&src)[N]) {
+    using W = typename RawWord<sizeof(T) * N>::type;
+    union {
+        W w;
+        Pack<T, N> pack;
+    } u;
+#pragma unroll
+    for (int i = 0; i < N; ++i) u.pack.v[i] = Traits<T>::from_ct(src[i]);
+    __stcs(reinterpret_cast<W *>(p), u.w);
+}
+
 // Round-to-nearest mul / sub that the compiler may NOT contract into an FMA: the reference writes
 // `x * w - 0.5` (kernels.py:145) and its CPU-interpreted golden vectors and our oracle evaluate it as two
 // rounded operations; keeping the same two roundings makes the cell index floor(x) bit-identical.

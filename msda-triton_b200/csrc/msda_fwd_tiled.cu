@@ -9,9 +9,12 @@
 
 namespace msda {
 
+// pyramid bytes of the slices gathered concurrently (one wave) -- well inside the 126 MB L2
+constexpr size_t kFwdL2Budget = 24u << 20;
+
 template <typename T, int LANES, int LK, bool BORDER, int NB, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
-    msda_fwd_tiled_kernel(const KernelArgs a, const int tiles_per_bh, const int total_tiles) {
+    msda_fwd_tiled_kernel(const KernelArgs a, const WaveSchedule ws) {
     using Cfg = TiledCfg<T, LANES, LK>;
     constexpr int VEC = Cfg::VEC, G = Cfg::G, PPL = Cfg::PPL;
     static_assert(LANES % NB == 0, "batch must divide the group");
@@ -29,25 +32,27 @@ __global__ void __launch_bounds__(THREADS, 1)
     const bool align = a.align != 0;
     const unsigned row_bytes = (unsigned)(a.H * a.D) * (unsigned)sizeof(T);
 
-    const int t_begin = (int)((long long)total_tiles * blockIdx.x / gridDim.x);
-    const int t_end = (int)((long long)total_tiles * (blockIdx.x + 1) / gridDim.x);
+    const int tiles_per_bh = ws.tiles_per_bh;
+    for (int wave = 0; wave < ws.waves; ++wave) {
+    int t_begin, t_end;
+    wave_range(ws, wave, blockIdx.x, gridDim.x, t_begin, t_end);
 
     int tile = t_begin + warp;
-    if (tile >= t_end) return;
+    if (tile >= t_end) continue;
 
     // software pipeline: sampling points / weights of the next warp tile are in flight while this one is processed
     TileUnit tu = decode_tile(tile, tiles_per_bh, g, G, a);
     float xy[2 * PPL], wa[PPL];
-    load_vec<T, 2 * PPL>(pts + ((size_t)tu.u * LK + j * PPL) * 2, xy);
-    load_vec<T, PPL>(aw + (size_t)tu.u * LK + j * PPL, wa);
+    load_vec_stream<T, 2 * PPL>(pts + ((size_t)tu.u * LK + j * PPL) * 2, xy);
+    load_vec_stream<T, PPL>(aw + (size_t)tu.u * LK + j * PPL, wa);
 
     for (; tile < t_end; tile += nwarps) {
         const int tile_n = tile + nwarps;
         const bool has_next = tile_n < t_end;
         const TileUnit tu_n = decode_tile(has_next ? tile_n : tile, tiles_per_bh, g, G, a);
         float xy_n[2 * PPL], wa_n[PPL];
-        load_vec<T, 2 * PPL>(pts + ((size_t)tu_n.u * LK + j * PPL) * 2, xy_n);
-        load_vec<T, PPL>(aw + (size_t)tu_n.u * LK + j * PPL, wa_n);
+        load_vec_stream<T, 2 * PPL>(pts + ((size_t)tu_n.u * LK + j * PPL) * 2, xy_n);
+        load_vec_stream<T, PPL>(aw + (size_t)tu_n.u * LK + j * PPL, wa_n);
 
         const unsigned char *__restrict__ lane_base =
             reinterpret_cast<const unsigned char *>(img + tu.bh_off + j * VEC);
@@ -105,7 +110,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                 }
             }
         }
-        if (tu.live) store_vec<T, VEC>(out + (size_t)tu.u * a.D + j * VEC, acc);
+        if (tu.live) store_vec_stream<T, VEC>(out + (size_t)tu.u * a.D + j * VEC, acc);
 
         tu = tu_n;
 #pragma unroll
@@ -113,6 +118,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll
         for (int i = 0; i < PPL; ++i) wa[i] = wa_n[i];
     }
+    }  // waves
 }
 
 template <typename T, int LANES, int LK>
@@ -125,10 +131,11 @@ static cudaError_t launch_tiled_t(const KernelArgs &a, int sm_count, cudaStream_
     const int warps = THREADS / 32;
     const int want = (total_tiles + warps - 1) / warps;
     const int grid = (int)(want < sm_count ? (want < 1 ? 1 : want) : sm_count);
+    const WaveSchedule ws = make_wave_schedule(a, tiles_per_bh, sizeof(T), kFwdL2Budget);
     if (a.border)
-        msda_fwd_tiled_kernel<T, LANES, LK, true, NB, THREADS><<<grid, THREADS, 0, st>>>(a, tiles_per_bh, total_tiles);
+        msda_fwd_tiled_kernel<T, LANES, LK, true, NB, THREADS><<<grid, THREADS, 0, st>>>(a, ws);
     else
-        msda_fwd_tiled_kernel<T, LANES, LK, false, NB, THREADS><<<grid, THREADS, 0, st>>>(a, tiles_per_bh, total_tiles);
+        msda_fwd_tiled_kernel<T, LANES, LK, false, NB, THREADS><<<grid, THREADS, 0, st>>>(a, ws);
     return cudaGetLastError();
 }
 

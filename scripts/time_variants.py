@@ -29,7 +29,7 @@ def timeit(fn, reps=20, warm=3):
     return ts[len(ts) // 2]
 
 
-for name in sys.argv[1:] or list(bench.WORKLOADS):
+for name in [a for a in sys.argv[1:] if not a.startswith('--')] or list(bench.WORKLOADS):
     B, Q, H, D, pyr, Kp, pm, ac = bench.WORKLOADS[name]
     t, s = bench.make_inputs(name, 0, device="cuda")
     fwd = timeit(lambda: K.b200_multi_scale_deformable_attention_fwd(t["img"], s, t["pts"], t["aw"], pm, ac))
@@ -37,6 +37,7 @@ for name in sys.argv[1:] or list(bench.WORKLOADS):
     for label, needs in (("bwd_all", (1, 1, 1)), ("bwd_img_only", (1, 0, 0)), ("bwd_no_img", (0, 1, 1))):
         res[label] = timeit(lambda: K.b200_multi_scale_deformable_attention_bwd(
             t["go"], t["img"], s, t["pts"], t["aw"], pm, ac, needs=needs, deterministic=False))
-    res["bwd_deterministic"] = timeit(lambda: K.b200_multi_scale_deformable_attention_bwd(
+    if "--nodet" not in sys.argv:
+      res["bwd_deterministic"] = timeit(lambda: K.b200_multi_scale_deformable_attention_bwd(
         t["go"], t["img"], s, t["pts"], t["aw"], pm, ac, deterministic=True), reps=5)
     print(name, {k: round(v, 4) for k, v in res.items()})
