@@ -440,8 +440,15 @@ __global__ void __launch_bounds__(THREADS, 1)
         __syncthreads();
         {
             float *__restrict__ gimg_rows = gimg + st_bh_off + (size_t)base_row * a.H * a.D + j * VEC;
+            const unsigned group_mask = (LANES == 32 ? 0xffffffffu : ((1u << LANES) - 1u)) << (g * LANES);
             for (int r = threadIdx.x / LANES; r < nrows; r += NGROUPS) {
-                unsigned idx = s_head[r];
+                // the group leader pops the whole list (read + reset in one lane: no intra-group read/write hazard)
+                unsigned idx = END;
+                if (j == 0) {
+                    idx = s_head[r];
+                    s_head[r] = END;
+                }
+                idx = __shfl_sync(group_mask, idx, g * LANES);
                 if (idx != END) {
                     float acc[VEC];
 #pragma unroll
@@ -456,7 +463,6 @@ __global__ void __launch_bounds__(THREADS, 1)
                         idx = nxt;
                     } while (idx != END);
                     red_add_vec<VEC>(gimg_rows + (size_t)r * a.H * a.D, acc);
-                    if (j == 0) s_head[r] = END;
                 }
             }
         }

@@ -119,6 +119,13 @@ def b200_multiscale_deformable_attention(
         # the kernels take one storage dtype; mixed inputs are promoted (under autocast custom_fwd casts to fp32)
         common = torch.promote_types(torch.promote_types(img.dtype, sampling_points.dtype), attention_weights.dtype)
         img, sampling_points, attention_weights = (t.to(common) for t in (img, sampling_points, attention_weights))
+    if torch.compiler.is_compiling():
+        # traced programs use the torch.library custom op (fake kernels + autograd formula, no graph break)
+        from .ops import multiscale_deformable_attention_op
+        if torch.is_autocast_enabled("cuda"):
+            img, sampling_points, attention_weights = (t.float() for t in (img, sampling_points, attention_weights))
+        return multiscale_deformable_attention_op(
+            img, img_shapes, sampling_points, attention_weights, padding_mode, bool(align_corners))
     return _B200MsdaFunction.apply(img, img_shapes, sampling_points, attention_weights, padding_mode, bool(align_corners))
 
 

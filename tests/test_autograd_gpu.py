@@ -148,3 +148,31 @@ def test_host_pipeline_matches_device_path():
     assert torch.equal(h_gi, gi.cpu())
     with pytest.raises(ValueError):
         pipe.run(img, s.cuda(), pin[1], pin[2], "zeros", False, h_out)      # unpinned input
+
+
+def test_torch_library_op_and_compile():
+    """torch.ops.msda_b200.forward: opcheck (schema, fake kernel, autograd registration) and a fullgraph compile."""
+    import msda_triton
+    from msda_triton.ops import multiscale_deformable_attention_op
+    img, s, pts, aw, go = (t.cuda() for t in make_inputs(2, 128, 8, 32, BENCH_PYRAMID, 4, seed=23))
+    a, b, c = (t.clone().requires_grad_(True) for t in (img, pts, aw))
+    torch.library.opcheck(torch.ops.msda_b200.forward.default, (a, s, b, c, "zeros", False),
+                          test_utils=("test_schema", "test_faketensor", "test_autograd_registration"))
+
+    def model(img, pts, aw):
+        out = msda_triton.multiscale_deformable_attention(img * 1.0, s, pts, aw, "zeros", False)
+        return out.sum(dim=-1)
+
+    eager = model(a, b, c)
+    eager.backward(go.sum(-1))
+    want = [eager.detach().clone(), a.grad.clone(), b.grad.clone(), c.grad.clone()]
+    a.grad = b.grad = c.grad = None
+    compiled = torch.compile(model, backend="aot_eager", fullgraph=True)
+    got = compiled(a, b, c)
+    got.backward(go.sum(-1))
+    torch.testing.assert_close(got, want[0], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(b.grad, want[2], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(c.grad, want[3], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(a.grad, want[1], rtol=1e-4, atol=1e-4)
+    out2 = multiscale_deformable_attention_op(img, s, pts, aw, "zeros", False)
+    assert torch.equal(out2, msda_triton.multiscale_deformable_attention(img, s, pts, aw, "zeros", False))
