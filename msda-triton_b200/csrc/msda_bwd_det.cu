@@ -4,7 +4,8 @@
 // summation order -- and therefore the low bits of grad_img -- changes from run to run.  This path produces
 // bit-identical grad_img on every run:
 //   1. keys   : every bilinear corner (unit, point, corner) emits key = destination row (b, pixel, h) and
-//               value = its own index; invalid (zeros-mode, out-of-range) corners get the sentinel key 0xFFFFFFFF.
+//               value = its own index; invalid (zeros-mode, out-of-range) corners get the sentinel key B*Npix*H (one past
+//               the last row), so only ceil(log2(rows+1)) key bits need sorting.
 //   2. sort   : stable LSD radix sort by key (cub::DeviceRadixSort, deterministic), so inside a segment the
 //               contributions are ordered by (unit, point, corner).
 //   3. reduce : one lane group per destination row walks its segment IN THAT ORDER, recomputes the corner weight
@@ -18,11 +19,11 @@
 
 namespace msda {
 
-constexpr unsigned kDetSentinel = 0xFFFFFFFFu;
 
 template <typename T>
 __global__ void __launch_bounds__(256) det_keys_kernel(const KernelArgs a, unsigned *__restrict__ keys,
-                                                       unsigned *__restrict__ vals, const long long n_points) {
+                                                       unsigned *__restrict__ vals, const long long n_points,
+                                                       const unsigned sentinel) {
     using CT = typename Traits<T>::CT;
     extern __shared__ __align__(16) unsigned char s_raw[];
     Level *s_lv = reinterpret_cast<Level *>(s_raw);
@@ -47,7 +48,7 @@ __global__ void __launch_bounds__(256) det_keys_kernel(const KernelArgs a, unsig
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const unsigned long long key = ((unsigned long long)b * a.Npix + rows[c]) * a.H + h;
-            kk[c] = ((mask >> c) & 1u) ? (unsigned)key : kDetSentinel;
+            kk[c] = ((mask >> c) & 1u) ? (unsigned)key : sentinel;
             vv[c] = (unsigned)(4 * i + c);
         }
         reinterpret_cast<uint4 *>(keys)[i] = k4;
@@ -55,7 +56,9 @@ __global__ void __launch_bounds__(256) det_keys_kernel(const KernelArgs a, unsig
     }
 }
 
-// One group of `lanes` lanes per destination row; lane j owns VEC channels of each chunk.
+// One WARP per destination row.  The warp's 32/lanes lane groups take the row's contributions round-robin (group t
+// handles positions lo+t, lo+t+T, ... of the sorted segment, two at a time for memory-level parallelism); the group
+// partials are then combined by a fixed butterfly, so the summation order depends only on the sorted order.
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) det_reduce_kernel(const KernelArgs a, const unsigned *__restrict__ keys,
                                                          const unsigned *__restrict__ vals, const long long n,
@@ -69,13 +72,33 @@ __global__ void __launch_bounds__(256) det_reduce_kernel(const KernelArgs a, con
     const T *__restrict__ gout = static_cast<const T *>(a.gout);
     T *__restrict__ gimg = static_cast<T *>(a.gimg);
     const int lanes = a.lanes;
-    const int j = threadIdx.x & (lanes - 1);
-    const int groups_per_cta = blockDim.x / lanes;
+    const int lane = threadIdx.x & 31;
+    const int j = lane & (lanes - 1);
+    const int team = lane / lanes, teams = 32 / lanes;
     const bool border = a.border != 0, align = a.align != 0;
+    const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long warps_total = ((long long)gridDim.x * blockDim.x) >> 5;
 
-    for (long long r = (long long)blockIdx.x * groups_per_cta + threadIdx.x / lanes; r < n_rows;
-         r += (long long)gridDim.x * groups_per_cta) {
-        // lower_bound(keys, r): first contribution of this row (all lanes of the group search redundantly)
+    auto contribution = [&](long long i, int c0, CT (&acc)[VEC]) {
+        const unsigned v = vals[i];
+        const int c = (int)(v & 3u);
+        const long long pi = (long long)(v >> 2);  // (unit, point) index
+        const long long u = pi / a.LK;
+        const int p = (int)(pi - u * a.LK);
+        CT xy[2];
+        load_vec<T, 2>(pts + 2 * pi, xy);
+        const Tap<CT> t = locate<CT>(xy[0], xy[1], s_lv[p / a.K], border, align);
+        const CT wx = (c & 1) ? t.dx : (CT)1 - t.dx;
+        const CT wy = (c & 2) ? t.dy : (CT)1 - t.dy;
+        const CT w = Traits<T>::to_ct(aw[pi]) * (wy * wx);
+        CT go[VEC];
+        load_vec<T, VEC>(gout + (size_t)u * a.D + c0, go);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc[e] += go[e] * w;
+    };
+
+    for (long long r = warp_global; r < n_rows; r += warps_total) {
+        // lower_bound(keys, r): first contribution of this row (every lane searches redundantly)
         long long lo = 0, hi = n;
         const unsigned key = (unsigned)r;
         while (lo < hi) {
@@ -84,28 +107,25 @@ __global__ void __launch_bounds__(256) det_reduce_kernel(const KernelArgs a, con
         }
         for (int chunk = 0; chunk < a.chunks; ++chunk) {
             const int c0 = (chunk * lanes + j) * VEC;
-            if (c0 >= a.D) continue;
-            CT acc[VEC];
+            const bool c_live = c0 < a.D;
+            CT acc0[VEC], acc1[VEC];
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) acc[e] = (CT)0;
-            for (long long i = lo; i < n && keys[i] == key; ++i) {
-                const unsigned v = vals[i];
-                const int c = (int)(v & 3u);
-                const long long pi = (long long)(v >> 2);         // (unit, point) index
-                const long long u = pi / a.LK;
-                const int p = (int)(pi - u * a.LK);
-                CT xy[2];
-                load_vec<T, 2>(pts + 2 * pi, xy);
-                const Tap<CT> t = locate<CT>(xy[0], xy[1], s_lv[p / a.K], border, align);
-                const CT wx = (c & 1) ? t.dx : (CT)1 - t.dx;
-                const CT wy = (c & 2) ? t.dy : (CT)1 - t.dy;
-                const CT w = Traits<T>::to_ct(aw[pi]) * (wy * wx);
-                CT go[VEC];
-                load_vec<T, VEC>(gout + (size_t)u * a.D + c0, go);
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) acc[e] += go[e] * w;
+            for (int e = 0; e < VEC; ++e) acc0[e] = acc1[e] = (CT)0;
+            if (c_live) {
+                long long i = lo + team;
+                for (; i + teams < n && keys[i + teams] == key; i += 2 * teams) {   // both i and i+teams in the row
+                    contribution(i, c0, acc0);
+                    contribution(i + teams, c0, acc1);
+                }
+                if (i < n && keys[i] == key) contribution(i, c0, acc0);
             }
-            store_vec<T, VEC>(gimg + (size_t)r * a.D + c0, acc);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                CT v = acc0[e] + acc1[e];
+                for (int m = lanes; m < 32; m <<= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+                acc0[e] = v;
+            }
+            if (c_live && team == 0) store_vec<T, VEC>(gimg + (size_t)r * a.D + c0, acc0);
         }
     }
 }
@@ -148,14 +168,15 @@ static cudaError_t launch_det_t(const KernelArgs &a, int vec, void *workspace, i
     size_t temp_bytes = det_sort_temp_bytes(n);
     const size_t smem = sizeof(Level) * (size_t)a.L;
 
-    det_keys_kernel<T><<<grid_for(n_points, 256, sm_count), 256, smem, st>>>(a, keys_in, vals_in, n_points);
+    int key_bits = 1;
+    while (key_bits < 32 && (1ull << key_bits) <= (unsigned long long)n_rows) ++key_bits;   // keys in [0, n_rows]
+    det_keys_kernel<T><<<grid_for(n_points, 256, sm_count), 256, smem, st>>>(a, keys_in, vals_in, n_points,
+                                                                           (unsigned)n_rows);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    // keys are < B*Npix*H or the all-ones sentinel: sort on all 32 bits
-    e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, n, 0, 32, st);
+    e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, n, 0, key_bits, st);
     if (e != cudaSuccess) return e;
-    const int groups_per_cta = 256 / a.lanes;
-    const int grid = grid_for(n_rows, groups_per_cta, sm_count);
+    const int grid = grid_for(n_rows, 256 / 32, sm_count);   // one warp per destination row
     switch (vec) {
         case 8:
             if constexpr (Traits<T>::kMaxVec >= 8) det_reduce_kernel<T, 8><<<grid, 256, smem, st>>>(a, keys_out, vals_out, n, n_rows);
