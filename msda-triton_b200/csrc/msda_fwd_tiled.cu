@@ -121,9 +121,8 @@ __global__ void __launch_bounds__(THREADS, 1)
     }  // waves
 }
 
-template <typename T, int LANES, int LK>
-static cudaError_t launch_tiled_t(const KernelArgs &a, int sm_count, cudaStream_t st) {
-    constexpr int THREADS = 512, NB = 4;
+template <typename T, int LANES, int LK, int THREADS, int NB>
+static cudaError_t launch_tiled_cfg(const KernelArgs &a, int sm_count, cudaStream_t st) {
     constexpr int G = TiledCfg<T, LANES, LK>::G;
     if (!tiled_offsets_fit(a, sizeof(T))) return cudaErrorNotSupported;
     const int tiles_per_bh = (a.Q + G - 1) / G;
@@ -137,6 +136,19 @@ static cudaError_t launch_tiled_t(const KernelArgs &a, int sm_count, cudaStream_
     else
         msda_fwd_tiled_kernel<T, LANES, LK, false, NB, THREADS><<<grid, THREADS, 0, st>>>(a, ws);
     return cudaGetLastError();
+}
+
+// Launch shape.  Measured on B200 (cold L2, fp32 D=32): 1024 threads x 2-point gather batches (64 registers) versus
+// 512 threads x 4-point batches (128 registers): bench shape border 0.147 vs 0.142 ms, zeros 0.153 vs 0.163 ms,
+// DETR encoder 0.173 vs 0.209 ms -- more resident warps hide the L2 latency of the levels that do not fit L1.
+template <typename T, int LANES, int LK>
+static cudaError_t launch_tiled_t(const KernelArgs &a, int sm_count, cudaStream_t st) {
+    if (const char *e = std::getenv("MSDA_B200_FWD_VARIANT")) {   // tuning knob
+        if (std::atoi(e) == 1) return launch_tiled_cfg<T, LANES, LK, 512, 4>(a, sm_count, st);
+    }
+    // lanes that own 4 points (16-bit storage, D=32) keep more state: stay at 128 registers there
+    if constexpr (TiledCfg<T, LANES, LK>::PPL >= 4) return launch_tiled_cfg<T, LANES, LK, 512, 4>(a, sm_count, st);
+    return launch_tiled_cfg<T, LANES, LK, 1024, 2>(a, sm_count, st);
 }
 
 // Eligibility: L*K == 16, one pixel-row slice is LANES x 16 bytes with LANES in the instantiated set.
