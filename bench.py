@@ -319,6 +319,8 @@ def time_e2e(name, steps, warmup, dist_sync=None, pipelined=True):
     e0.record()
     for _ in range(steps):
         one_step()
+    if pipelined:
+        torch.cuda.current_stream().wait_stream(pipe.d2h)   # the timed region ends when the last result is on the host
     e1.record()
     torch.cuda.synchronize()
     if dist_sync:

@@ -32,6 +32,7 @@ class HostMsda:
         self.backward = backward
         self.h2d = torch.cuda.Stream(self.device)
         self.d2h = torch.cuda.Stream(self.device)
+        self._staging_free = None   # event: the kernels of the previous run() have finished reading the staging buffers
 
     @staticmethod
     def _check_pinned(*tensors):
@@ -43,16 +44,18 @@ class HostMsda:
             out, out_grad=None, img_grad=None, sampling_points_grad=None, attention_weights_grad=None,
             deterministic: Optional[bool] = None):
         """All tensor arguments except ``img_shapes_dev`` (int64 [L,2] on the device) are pinned host tensors;
-        ``out`` / ``*_grad`` are filled in place.  Returns after the last D2H copy has been ENQUEUED; the caller's
-        current stream is made to wait for it (``torch.cuda.current_stream().synchronize()`` to read the results)."""
+        ``out`` / ``*_grad`` are filled in place.  Returns after the last D2H copy has been ENQUEUED on an internal
+        stream; call :meth:`synchronize` (or ``torch.cuda.synchronize()``) before reading the host buffers."""
         do_bwd = out_grad is not None
         if do_bwd and not self.backward:
             raise ValueError("this HostMsda was created with backward=False")
         self._check_pinned(img, sampling_points, attention_weights, out, out_grad, img_grad, sampling_points_grad,
                            attention_weights_grad)
         cur = torch.cuda.current_stream(self.device)
-        self.h2d.wait_stream(cur)     # staging buffers may still be read by earlier work on the caller's stream
-        self.d2h.wait_stream(cur)
+        # The staging buffers are free as soon as the previous run()'s KERNELS are done -- its D2H copies may still be
+        # in flight, so back-to-back calls overlap this call's H2D with the previous call's D2H (PCIe is full duplex).
+        if self._staging_free is not None:
+            self.h2d.wait_event(self._staging_free)
         needs = (img_grad is not None, sampling_points_grad is not None, attention_weights_grad is not None)
         for b in range(self.batch):
             sl = slice(b, b + 1)
@@ -79,5 +82,9 @@ class HostMsda:
                     if dst is not None and src is not None:
                         dst[sl].copy_(src, non_blocking=True)
                         src.record_stream(self.d2h)
-        cur.wait_stream(self.d2h)
+        self._staging_free = cur.record_event()
         return out
+
+    def synchronize(self) -> None:
+        """Blocks the host until every result of the previous run() calls has landed in the host buffers."""
+        self.d2h.synchronize()

@@ -138,9 +138,9 @@ def test_host_pipeline_matches_device_path():
     h_out = torch.empty(3, 500, 8, 32).pin_memory()
     h_gi, h_gp, h_ga = (torch.empty_like(t).pin_memory() for t in (img, pts, aw))
     pipe = HostMsda(3, img.shape[1], 8, 32, 500, 4, 4)
-    for _ in range(2):
+    for _ in range(3):      # back-to-back calls overlap (H2D of call i+1 with D2H of call i)
         pipe.run(pin[0], s.cuda(), pin[1], pin[2], "zeros", False, h_out, pin[3], h_gi, h_gp, h_ga, deterministic=True)
-        torch.cuda.synchronize()
+    pipe.synchronize()
     d = [t.cuda() for t in (img, s, pts, aw, go)]
     out = K.b200_multi_scale_deformable_attention_fwd(d[0], d[1], d[2], d[3], "zeros", False)
     gi, gp, ga = K.b200_multi_scale_deformable_attention_bwd(d[4], d[0], d[1], d[2], d[3], "zeros", False, deterministic=True)
