@@ -511,8 +511,10 @@ static cudaError_t launch_tiled_t(const KernelArgs &a, int sm_count, cudaStream_
     return cudaGetLastError();
 }
 
-// MSDA_B200_BWD_BINNED selects the experimental binned kernel: unset/0 = plain atomics kernel (default),
-// 1 = super-tiles of 256 queries binning up to 1408 rows, 2 = 256 queries / 320 rows, 3 = 128 queries / 1408 rows.
+// MSDA_B200_BWD_BINNED selects the experimental binned kernels: unset/0 = plain atomics kernel (default),
+// 1 = super-tiles of 256 queries binning up to 1408 rows, 2 = 256 queries / 320 rows, 3 = 128 queries / 1408 rows,
+// 4 = split backward (K1 = this file's plain kernel without grad_img, K2 = msda_bwd_scatter.cu: 0.19 + 0.29 ms on the
+// bench shape versus 0.47 ms fused -- K2's list walk costs ~240 warp instructions per unit).
 // Measured on B200 (profiles/r1_ncu_summary.md): `red` sectors drop to 40 %, but the shared-memory footprint
 // shrinks L1 (gather hit rate 66 % -> 40 %) and the net effect is within +-8 % of the plain kernel, so it is opt-in.
 static int binned_variant() {
@@ -523,6 +525,20 @@ static int binned_variant() {
 cudaError_t launch_backward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st) {
     if (a.LK != 16 || a.L > 16) return cudaErrorNotSupported;
     const int variant = binned_variant();
+    if ((a.flags & kNeedImg) && variant == 4 && dtype == 0 && a.D == 32) {
+        // split backward: K1 = grad_points / grad_weights (gathers, L1 for the pyramid), K2 = grad_img (no gathers)
+        KernelArgs k1 = a;
+        k1.flags &= ~kNeedImg;
+        if (k1.flags) {
+            const cudaError_t e1 = launch_tiled_t<float, 8, 16>(k1, sm_count, st);
+            if (e1 != cudaSuccess) return e1;
+        }
+        const cudaError_t e2 = launch_backward_scatter(a, dtype, sm_count, st);
+        if (e2 != cudaErrorNotSupported) return e2;
+        KernelArgs k2 = a;
+        k2.flags = kNeedImg;
+        return launch_tiled_t<float, 8, 16>(k2, sm_count, st);
+    }
     if ((a.flags & kNeedImg) && variant != 0 && dtype == 0 && a.D == 32) {
         switch (variant) {
             case 1: return launch_binned_t<float, 8, 16, 4, 1408>(a, sm_count, st);

@@ -15,6 +15,9 @@ cudaError_t launch_backward_generic(const KernelArgs &a, int dtype, int vec, int
 cudaError_t launch_forward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st);
 cudaError_t launch_backward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st);
 
+// grad_img alone, without gathers (split backward; msda_bwd_scatter.cu).  a.gimg = zero-filled fp32 accumulation image.
+cudaError_t launch_backward_scatter(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st);
+
 // Deterministic grad_img (sorted-segment reduction, msda_bwd_det.cu).  a.gimg = grad_img in STORAGE dtype.
 bool det_supported(const KernelArgs &a);
 size_t det_workspace_bytes(const KernelArgs &a);

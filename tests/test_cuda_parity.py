@@ -304,7 +304,7 @@ def test_deterministic_full_size_bitwise(K):
     assert_close(to_np(a), to_np(c), 1e-4, 1e-5 * float(c.abs().max()), "deterministic vs atomic")
 
 
-@pytest.mark.parametrize("variant", ["1", "2", "3"])
+@pytest.mark.parametrize("variant", ["1", "2", "3", "4"])
 @pytest.mark.parametrize("pm,ac", [("zeros", False), ("border", True)])
 def test_binned_backward_variants(K, oracle, variant, pm, ac):
     """The opt-in binned backward (in-CTA segmented reduction of the coarse levels) must match the oracle too."""
