@@ -316,3 +316,31 @@ def test_binned_backward_variants(K, oracle, variant, pm, ac):
         os.environ.pop("MSDA_B200_BWD_BINNED")
     ref = (oracle.forward(img, s, pts, aw, pm, ac),) + oracle.backward(go, img, s, pts, aw, pm, ac)
     check_against(test, ref, torch.float32, f"binned variant {variant}")
+
+
+@pytest.mark.parametrize("Kp", [4, 3], ids=["tuned", "generic"])
+def test_addressing_beyond_2_to_31_elements(K, Kp):
+    """B=400 DETR-size images: img has 2.27e9 elements (9.1 GB fp32), so element offsets exceed int32.  The last image
+    must give exactly what it gives when processed alone (same kernels, same per-unit arithmetic)."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40 << 30:
+        pytest.skip("needs ~30 GB of free device memory")
+    B, Q, H, D = 400, 8, 8, 32
+    npix = sum(h * w for h, w in DETR_PYRAMID)
+    g = torch.Generator(device="cuda").manual_seed(77)
+    img = torch.randn(B, npix, H, D, device="cuda", generator=g)
+    assert img.numel() > 2 ** 31
+    s = torch.tensor(DETR_PYRAMID, device="cuda")
+    pts = torch.rand(B, Q, H, 4, Kp, 2, device="cuda", generator=g)
+    aw = torch.rand(B, Q, H, 4, Kp, device="cuda", generator=g)
+    go = torch.rand(B, Q, H, D, device="cuda", generator=g)
+    out = K.b200_multi_scale_deformable_attention_fwd(img, s, pts, aw, "zeros", False)
+    gi, gp, ga = K.b200_multi_scale_deformable_attention_bwd(go, img, s, pts, aw, "zeros", False)
+    for b in (0, B - 1):
+        sl = slice(b, b + 1)
+        out1 = K.b200_multi_scale_deformable_attention_fwd(img[sl], s, pts[sl], aw[sl], "zeros", False)
+        gi1, gp1, ga1 = K.b200_multi_scale_deformable_attention_bwd(go[sl], img[sl], s, pts[sl], aw[sl], "zeros", False)
+        assert torch.equal(out[sl], out1) and torch.equal(gp[sl], gp1) and torch.equal(ga[sl], ga1)
+        torch.testing.assert_close(gi[sl], gi1, rtol=1e-5, atol=1e-6)     # atomics: order may differ
+    del img, gi
+    torch.cuda.empty_cache()
