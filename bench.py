@@ -40,6 +40,10 @@ WORKLOADS = {
     "bench_q10k_zeros": (4, 10000, 8, 32, BENCH_PYRAMID, 4, "zeros", False),
     "detr_encoder_zeros": (2, 22223, 8, 32, DETR_PYRAMID, 4, "zeros", False),
     "train_b64_encoder_zeros": (64, 22223, 8, 32, DETR_PYRAMID, 4, "zeros", False),   # BASELINE configs[4], whole batch
+    "readme_q900_zeros": (2, 900, 8, 32, BENCH_PYRAMID, 4, "zeros", False),            # BASELINE configs[0] (README example)
+    # encoder self-attention with realistic locality: query q sits on pixel q of the pyramid and samples
+    # N(0, 2 px) around its own normalised position on every level (SURVEY.md 8d, M2 "encoder-realistic" variant)
+    "detr_encoder_local_zeros": (2, 22223, 8, 32, DETR_PYRAMID, 4, "zeros", False),
 }
 HEADLINE = "bench_q10k_border"
 METRIC = "MSDA fwd+bwd throughput, 10k-query benchmark shape (fp32)"
@@ -51,9 +55,20 @@ def make_inputs(name, seed, device="cpu", pin=False):
     g = torch.Generator().manual_seed(seed)
     L = len(pyr)
     npix = sum(h * w for h, w in pyr)
+    pts = torch.rand(B, Q, H, L, K, 2, generator=g)
+    if "local" in name:
+        # reference point = centre of the query's own pixel (queries enumerate the pyramid in storage order)
+        centres = []
+        for (h, w) in pyr:
+            ys, xs = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+            centres.append(torch.stack(((xs.reshape(-1) + 0.5) / w, (ys.reshape(-1) + 0.5) / h), dim=-1))
+        ref = torch.cat(centres)[:Q]                                                     # [Q, 2]
+        wh = torch.tensor([[w, h] for (h, w) in pyr], dtype=torch.float32)               # per level (w, h)
+        off = torch.randn(B, Q, H, L, K, 2, generator=g) * 2.0 / wh[None, None, None, :, None, :]
+        pts = ref[None, :, None, None, None, :] + off
     t = {
         "img": torch.randn(B, npix, H, D, generator=g),
-        "pts": torch.rand(B, Q, H, L, K, 2, generator=g),
+        "pts": pts,
         "aw": torch.softmax(torch.randn(B, Q, H, L, K, generator=g), dim=-1),
         "go": torch.rand(B, Q, H, D, generator=g),
     }
@@ -231,14 +246,15 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------------------
-def time_workload(name, steps, warmup, K, flush, dist_sync=None, clock_index=None):
-    """Returns dict with per-step mean ms for fwd, bwd, total (device events, cold L2)."""
+def time_workload(name, steps, warmup, K, flush, dist_sync=None, clock_index=None, cold=True):
+    """Returns dict with per-step mean ms for fwd, bwd, total (device events; cold L2 unless cold=False)."""
     B, Q, H, D, pyr, Kp, pm, ac = WORKLOADS[name]
     t, shapes = make_inputs(name, seed=0, device="cuda")
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
 
     def one_step(e=None):
-        flush.fill_(1.0)                      # cold L2: 256 MiB written between steps, outside the event pair
+        if cold:
+            flush.fill_(1.0)                  # cold L2: 256 MiB written between steps, outside the event pair
         if e:
             e[0].record()
         out = K.b200_multi_scale_deformable_attention_fwd(t["img"], shapes, t["pts"], t["aw"], pm, ac)
@@ -478,6 +494,9 @@ def run_ours(args):
                                "fwd_hbm_frac": bmn["fwd"] / (r["fwd_ms"] * 1e-3) / 1e9 / peak,
                                "bwd_hbm_frac": bmn["bwd"] / (r["bwd_ms"] * 1e-3) / 1e9 / peak,
                                "fwd_gather_gbs": bmn["gather"] / (r["fwd_ms"] * 1e-3) / 1e9}
+            warm = time_workload(HEADLINE, max(5, args.steps // 4), 3, K, flush, cold=False)
+            extra["headline_warm_l2"] = {"fwd_ms": warm["fwd_ms"], "bwd_ms": warm["bwd_ms"],
+                                         "note": "back-to-back steps without the L2 flush"}
             try:
                 extra["gdino_decoder_module_bf16"] = time_module(flush)
             except Exception as ex:  # noqa: BLE001
