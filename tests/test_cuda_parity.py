@@ -304,18 +304,19 @@ def test_deterministic_full_size_bitwise(K):
     assert_close(to_np(a), to_np(c), 1e-4, 1e-5 * float(c.abs().max()), "deterministic vs atomic")
 
 
-@pytest.mark.parametrize("variant", ["1", "2", "3", "4"])
 @pytest.mark.parametrize("pm,ac", [("zeros", False), ("border", True)])
-def test_binned_backward_variants(K, oracle, variant, pm, ac):
-    """The opt-in binned backward (in-CTA segmented reduction of the coarse levels) must match the oracle too."""
+def test_split_backward_variant(K, oracle, pm, ac):
+    """The opt-in split backward (K1 without grad_img + scatter-only K2 with in-CTA binning) must match the oracle."""
     img, s, pts, aw, go = make_inputs(2, 700, 8, 32, BENCH_PYRAMID, 4, seed=17, points="wide", weights="softmax_lk")
-    os.environ["MSDA_B200_BWD_BINNED"] = variant
+    os.environ["MSDA_B200_BWD_SPLIT"] = "1"
     try:
         test = run_cuda(K, img, s, pts, aw, go, pm, ac)
+        only_img = run_cuda(K, img, s, pts, aw, go, pm, ac, needs=(True, False, False))
     finally:
-        os.environ.pop("MSDA_B200_BWD_BINNED")
+        os.environ.pop("MSDA_B200_BWD_SPLIT")
     ref = (oracle.forward(img, s, pts, aw, pm, ac),) + oracle.backward(go, img, s, pts, aw, pm, ac)
-    check_against(test, ref, torch.float32, f"binned variant {variant}")
+    check_against(test, ref, torch.float32, "split backward")
+    assert_close(to_np(only_img[1]), ref[1], 1e-4, 1e-5 * np.abs(ref[1]).max(), "split backward, grad_img only")
 
 
 @pytest.mark.parametrize("Kp", [4, 3], ids=["tuned", "generic"])
