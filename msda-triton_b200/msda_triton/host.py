@@ -7,8 +7,8 @@ The reference has no equivalent (its tensors are expected on the device already)
     H2D(chunk i+1)   ||   kernels(chunk i)   ||   D2H(chunk i-1)
 
 so a step costs about max(H2D, D2H) + one chunk of compute instead of H2D + compute + D2H (PCIe is full duplex).
-Chunks are whole images because ``grad_img`` couples all queries of one image.  Device staging buffers are allocated
-once per :class:`HostMsda` and reused.
+Chunks are whole images because ``grad_img`` couples all queries of one image.  Two sets of device staging buffers are
+allocated once per :class:`HostMsda` and used alternately.
 """
 from __future__ import annotations
 
@@ -24,15 +24,23 @@ class HostMsda:
                  dtype: torch.dtype = torch.float32, device: Optional[torch.device] = None, backward: bool = True):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         d = dict(dtype=dtype, device=self.device)
-        self.img = torch.empty((batch, num_pixels, heads, channels), **d)
-        self.pts = torch.empty((batch, queries, heads, levels, points, 2), **d)
-        self.aw = torch.empty((batch, queries, heads, levels, points), **d)
-        self.go = torch.empty((batch, queries, heads, channels), **d) if backward else None
+
+        def staging():
+            return {
+                "img": torch.empty((batch, num_pixels, heads, channels), **d),
+                "pts": torch.empty((batch, queries, heads, levels, points, 2), **d),
+                "aw": torch.empty((batch, queries, heads, levels, points), **d),
+                "go": torch.empty((batch, queries, heads, channels), **d) if backward else None,
+                "free": None,   # event: the kernels that read this staging set have finished
+            }
+
+        # two staging sets: the H2D copies of call i+1 never wait for the kernels of call i
+        self._sets = [staging(), staging()]
+        self._turn = 0
         self.batch = batch
         self.backward = backward
         self.h2d = torch.cuda.Stream(self.device)
         self.d2h = torch.cuda.Stream(self.device)
-        self._staging_free = None   # event: the kernels of the previous run() have finished reading the staging buffers
 
     @staticmethod
     def _check_pinned(*tensors):
@@ -52,27 +60,29 @@ class HostMsda:
         self._check_pinned(img, sampling_points, attention_weights, out, out_grad, img_grad, sampling_points_grad,
                            attention_weights_grad)
         cur = torch.cuda.current_stream(self.device)
-        # The staging buffers are free as soon as the previous run()'s KERNELS are done -- its D2H copies may still be
-        # in flight, so back-to-back calls overlap this call's H2D with the previous call's D2H (PCIe is full duplex).
-        if self._staging_free is not None:
-            self.h2d.wait_event(self._staging_free)
+        st = self._sets[self._turn]
+        self._turn ^= 1
+        # A staging set is free as soon as the KERNELS of the call that used it last are done -- that call's D2H copies
+        # may still be in flight, so back-to-back calls overlap this call's H2D with earlier D2H (PCIe is full duplex).
+        if st["free"] is not None:
+            self.h2d.wait_event(st["free"])
         needs = (img_grad is not None, sampling_points_grad is not None, attention_weights_grad is not None)
         for b in range(self.batch):
             sl = slice(b, b + 1)
             with torch.cuda.stream(self.h2d):
-                self.img[sl].copy_(img[sl], non_blocking=True)
-                self.pts[sl].copy_(sampling_points[sl], non_blocking=True)
-                self.aw[sl].copy_(attention_weights[sl], non_blocking=True)
+                st["img"][sl].copy_(img[sl], non_blocking=True)
+                st["pts"][sl].copy_(sampling_points[sl], non_blocking=True)
+                st["aw"][sl].copy_(attention_weights[sl], non_blocking=True)
                 if do_bwd:
-                    self.go[sl].copy_(out_grad[sl], non_blocking=True)
+                    st["go"][sl].copy_(out_grad[sl], non_blocking=True)
                 ready = self.h2d.record_event()
             cur.wait_event(ready)
             o = kernels.b200_multi_scale_deformable_attention_fwd(
-                self.img[sl], img_shapes_dev, self.pts[sl], self.aw[sl], padding_mode, align_corners)
+                st["img"][sl], img_shapes_dev, st["pts"][sl], st["aw"][sl], padding_mode, align_corners)
             grads = (None, None, None)
             if do_bwd and any(needs):
                 grads = kernels.b200_multi_scale_deformable_attention_bwd(
-                    self.go[sl], self.img[sl], img_shapes_dev, self.pts[sl], self.aw[sl], padding_mode, align_corners,
+                    st["go"][sl], st["img"][sl], img_shapes_dev, st["pts"][sl], st["aw"][sl], padding_mode, align_corners,
                     needs=needs, deterministic=deterministic)
             done = cur.record_event()
             self.d2h.wait_event(done)
@@ -82,7 +92,7 @@ class HostMsda:
                     if dst is not None and src is not None:
                         dst[sl].copy_(src, non_blocking=True)
                         src.record_stream(self.d2h)
-        self._staging_free = cur.record_event()
+        st["free"] = cur.record_event()
         return out
 
     def synchronize(self) -> None:
