@@ -498,9 +498,13 @@ def run_ours(args):
             extra["headline_warm_l2"] = {"fwd_ms": warm["fwd_ms"], "bwd_ms": warm["bwd_ms"],
                                          "note": "back-to-back steps without the L2 flush"}
             try:
-                extra["gdino_decoder_module_bf16"] = time_module(flush)
+                extra["gdino_decoder_module_bf16"] = time_module(flush)                      # fused module core
+                os.environ["MSDA_B200_FUSED_MODULE"] = "0"
+                extra["gdino_decoder_module_bf16_composed"] = time_module(flush)             # softmax etc. in torch
             except Exception as ex:  # noqa: BLE001
                 extra["gdino_decoder_module_bf16"] = {"error": str(ex)}
+            finally:
+                os.environ.pop("MSDA_B200_FUSED_MODULE", None)
             qps, ms_img, threads, sample = cpu_route_sample(HEADLINE, reps=10, warm=1)
             cpu = {"value": qps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                    "ms_per_image": ms_img}

@@ -60,7 +60,8 @@ enum msda_bwd_flags {
     MSDA_BWD_NEED_POINTS = 2,   /* produce grad_sampling_points (ctx.needs_input_grad[2]) */
     MSDA_BWD_NEED_WEIGHTS = 4,  /* produce grad_attention_weights (ctx.needs_input_grad[3]) */
     MSDA_BWD_NEED_ALL = 7,
-    MSDA_BWD_DETERMINISTIC = 8  /* grad_img by sorted-segment reduction instead of atomics (bit-reproducible) */
+    MSDA_BWD_DETERMINISTIC = 8, /* grad_img by sorted-segment reduction instead of atomics (bit-reproducible) */
+    MSDA_BWD_NEED_REF = 16      /* msda_module_backward only: produce grad_reference_points */
 };
 
 enum msda_error {
@@ -115,6 +116,28 @@ size_t msda_backward_workspace_bytes(const msda_problem *prob, int flags);
 int msda_backward(void *grad_img, void *grad_points, void *grad_weights, const void *grad_out, const void *img,
                   const int64_t *img_shapes, const void *sampling_points, const void *attention_weights,
                   const msda_problem *prob, int flags, void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * Fused module core -- the part of MultiscaleDeformableAttention.forward between the projections
+ * (src/msda_triton/frontend.py:253-289): softmax of the attention logits over L*K, sampling_points =
+ * reference + offset / level shape (2-d references; x is divided by the level HEIGHT and y by the WIDTH exactly as the
+ * reference does, frontend.py:272-276) or reference_xy + offset * reference_wh / (2K) (4-d, frontend.py:278-282),
+ * then the MSDA operator -- in ONE kernel, without materialising sampling_points / attention_weights.
+ *   value  [B, Npix, H, D]        projected pyramid
+ *   proj   [B, Q, H, L, K, 3]     query projection viewed as (offset x, offset y, attention logit) triples
+ *   ref    [B, Q, ref_dim]        reference points, ref_dim = 2 or 4
+ * msda_module_supported returns 1 when the fused kernels cover `prob` (fp32/fp16/bf16, D == 32, L*K == 16); otherwise
+ * the caller composes the unfused pieces (softmax etc. + msda_forward).
+ * Backward flags: MSDA_BWD_NEED_IMG -> grad_value, NEED_POINTS|NEED_WEIGHTS -> grad_proj, NEED_REF -> grad_ref.
+ * grad_ref is an fp32 [B, Q, ref_dim] buffer regardless of the storage dtype; the library zero-fills it and grad_value.
+ * Workspace: msda_backward_workspace_bytes(prob, flags) (fp32 accumulation image for 16-bit storage).
+ */
+int msda_module_supported(const msda_problem *prob, int ref_dim);
+int msda_module_forward(void *out, const void *value, const int64_t *img_shapes, const void *proj, const void *ref,
+                        int ref_dim, const msda_problem *prob, void *stream);
+int msda_module_backward(void *grad_value, void *grad_proj, float *grad_ref, const void *grad_out, const void *value,
+                         const int64_t *img_shapes, const void *proj, const void *ref, int ref_dim,
+                         const msda_problem *prob, int flags, void *workspace, size_t workspace_bytes, void *stream);
 
 /*
  * Device-side level preprocessing (kernels.py:44-64): table[l] = {h_l, w_l, offset_l, 0} as int32, plus

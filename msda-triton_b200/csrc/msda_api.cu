@@ -10,6 +10,7 @@
 #include "../../include/msda_b200.h"
 #include "msda_common.cuh"
 #include "msda_launch.h"
+#include "msda_tiled.cuh"
 
 namespace {
 
@@ -286,6 +287,116 @@ int msda_backward(void *grad_img, void *grad_points, void *grad_weights, const v
     if (staged) {
         e = msda::launch_round_grad_img(grad_img, static_cast<const float *>(accum), (long long)img_elems, prob->dtype, st);
         if (e != cudaSuccess) return fail_cuda(e, "msda_backward grad_img rounding");
+    }
+    return MSDA_OK;
+}
+
+int msda_module_supported(const msda_problem *prob, int ref_dim) {
+    if (validate(prob) != MSDA_OK) return 0;
+    if (ref_dim != 2 && ref_dim != 4) return 0;
+    if (prob->dtype == MSDA_DTYPE_F64 || prob->D != 32 || prob->L * prob->K != 16 || prob->L > 16) return 0;
+    msda::KernelArgs a;
+    fill_args(a, prob, 1);
+    return msda::tiled_offsets_fit(a, dtype_size(prob->dtype)) ? 1 : 0;
+}
+
+int msda_module_forward(void *out, const void *value, const int64_t *img_shapes, const void *proj, const void *ref,
+                        int ref_dim, const msda_problem *prob, void *stream) {
+    int rc = validate(prob);
+    if (rc != MSDA_OK) return rc;
+    if (!msda_module_supported(prob, ref_dim))
+        return fail(MSDA_ERR_BAD_SHAPE, "msda_module_forward: unsupported problem (needs fp32/fp16/bf16, D == 32, "
+                                        "L*K == 16, ref_dim 2 or 4); use msda_forward on materialised operands");
+    if (prob->B == 0 || prob->Q == 0) return MSDA_OK;
+    if (!out || !value || !img_shapes || !proj || !ref)
+        return fail(MSDA_ERR_NULL_POINTER, "msda_module_forward: NULL device pointer");
+    const size_t es = dtype_size(prob->dtype);
+    if (!aligned(value, 16) || !aligned(out, 16) || !aligned(proj, 8) || !aligned(ref, 2 * es) || !aligned(img_shapes, 8))
+        return fail(MSDA_ERR_BAD_SHAPE, "msda_module_forward: value/out must be 16-byte, proj 8-byte aligned");
+    DeviceInfo dev;
+    rc = device_info(&dev);
+    if (rc != MSDA_OK) return rc;
+    msda::KernelArgs a;
+    fill_args(a, prob, (int)(16 / es));
+    a.img = value;
+    a.shapes = reinterpret_cast<const long long *>(img_shapes);
+    a.proj = proj;
+    a.ref = ref;
+    a.ref_dim = ref_dim;
+    a.out = out;
+    cudaError_t e = msda::launch_module_forward_tiled(a, prob->dtype, dev.sm_count, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail_cuda(e, "msda_module_forward launch");
+    return MSDA_OK;
+}
+
+int msda_module_backward(void *grad_value, void *grad_proj, float *grad_ref, const void *grad_out, const void *value,
+                         const int64_t *img_shapes, const void *proj, const void *ref, int ref_dim,
+                         const msda_problem *prob, int flags, void *workspace, size_t workspace_bytes, void *stream) {
+    int rc = validate(prob);
+    if (rc != MSDA_OK) return rc;
+    if (!msda_module_supported(prob, ref_dim))
+        return fail(MSDA_ERR_BAD_SHAPE, "msda_module_backward: unsupported problem (see msda_module_supported)");
+    if (flags & MSDA_BWD_DETERMINISTIC)
+        return fail(MSDA_ERR_BAD_MODE, "msda_module_backward: the deterministic mode is available through the unfused "
+                                       "path only (msda_backward)");
+    const bool need_img = flags & MSDA_BWD_NEED_IMG, need_proj = flags & (MSDA_BWD_NEED_POINTS | MSDA_BWD_NEED_WEIGHTS),
+               need_ref = flags & MSDA_BWD_NEED_REF;
+    if (!need_img && !need_proj && !need_ref) return MSDA_OK;
+    const size_t es = dtype_size(prob->dtype);
+    const size_t img_elems = (size_t)prob->B * prob->Npix * prob->H * prob->D;
+    const bool no_units = prob->B == 0 || prob->Q == 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DeviceInfo dev;
+    rc = device_info(&dev);
+    if (rc != MSDA_OK) return rc;
+    if ((need_img && !grad_value && img_elems > 0) || (!no_units && ((need_proj && !grad_proj) || (need_ref && !grad_ref))))
+        return fail(MSDA_ERR_NULL_POINTER, "msda_module_backward: a requested gradient buffer is NULL");
+
+    const bool staged = need_img && prob->dtype != MSDA_DTYPE_F32;
+    void *accum = grad_value;
+    size_t accum_bytes = img_elems * es;
+    if (staged) {
+        const size_t want = img_elems * sizeof(float);
+        if ((!workspace && want > 0) || workspace_bytes < want || !aligned(workspace, 16))
+            return fail(MSDA_ERR_WORKSPACE, "msda_module_backward: 16-byte aligned workspace of %zu bytes required, got %zu",
+                        want, workspace_bytes);
+        accum = workspace;
+        accum_bytes = want;
+    }
+    cudaError_t e;
+    if (need_img && img_elems > 0) {
+        e = cudaMemsetAsync(accum, 0, accum_bytes, st);
+        if (e != cudaSuccess) return fail_cuda(e, "msda_module_backward zero-fill");
+    }
+    if (need_ref && !no_units) {
+        e = cudaMemsetAsync(grad_ref, 0, sizeof(float) * (size_t)prob->B * prob->Q * ref_dim, st);
+        if (e != cudaSuccess) return fail_cuda(e, "msda_module_backward zero-fill of grad_ref");
+    }
+    if (no_units) return MSDA_OK;
+    if (!grad_out || !value || !img_shapes || !proj || !ref)
+        return fail(MSDA_ERR_NULL_POINTER, "msda_module_backward: NULL device pointer");
+    if (!aligned(value, 16) || !aligned(grad_out, 16) || !aligned(accum, 16) || !aligned(proj, 8) ||
+        !aligned(grad_proj, 8) || !aligned(ref, 2 * es) || !aligned(img_shapes, 8))
+        return fail(MSDA_ERR_BAD_SHAPE, "msda_module_backward: misaligned pointer");
+
+    msda::KernelArgs a;
+    fill_args(a, prob, (int)(16 / es));
+    a.img = value;
+    a.shapes = reinterpret_cast<const long long *>(img_shapes);
+    a.proj = proj;
+    a.ref = ref;
+    a.ref_dim = ref_dim;
+    a.gout = grad_out;
+    a.gimg = accum;
+    a.gproj = grad_proj;
+    a.gref = grad_ref;
+    a.flags = (need_img ? MSDA_BWD_NEED_IMG : 0) | (need_proj ? (MSDA_BWD_NEED_POINTS | MSDA_BWD_NEED_WEIGHTS) : 0) |
+              (need_ref ? MSDA_BWD_NEED_REF : 0);
+    e = msda::launch_module_backward_tiled(a, prob->dtype, dev.sm_count, st);
+    if (e != cudaSuccess) return fail_cuda(e, "msda_module_backward launch");
+    if (staged) {
+        e = msda::launch_round_grad_img(grad_value, static_cast<const float *>(accum), (long long)img_elems, prob->dtype, st);
+        if (e != cudaSuccess) return fail_cuda(e, "msda_module_backward grad_value rounding");
     }
     return MSDA_OK;
 }

@@ -34,7 +34,10 @@ template <int N, int STEP> __device__ __forceinline__ void transpose_reduce(floa
     }
 }
 
-template <typename T, int LANES, int LK, bool BORDER, int NB, int THREADS>
+// FUSED = backward of the module core: operands are the raw projection + reference points (see msda_tiled.cuh);
+// the epilogue turns (grad weight, grad point) into grad of the projection triples (softmax backward, 1/shape or
+// ref_wh/2K scaling) and accumulates grad of the reference points with a handful of scalar atomics per unit.
+template <typename T, int LANES, int LK, bool BORDER, int NB, int THREADS, bool FUSED>
 __global__ void __launch_bounds__(THREADS, 1)
     msda_bwd_tiled_kernel(const KernelArgs a, const WaveSchedule ws) {
     using Cfg = TiledCfg<T, LANES, LK>;
@@ -45,8 +48,6 @@ __global__ void __launch_bounds__(THREADS, 1)
     build_level_table(s_lv, a.shapes, a.L);
 
     const T *__restrict__ img = static_cast<const T *>(a.img);
-    const T *__restrict__ pts = static_cast<const T *>(a.pts);
-    const T *__restrict__ aw = static_cast<const T *>(a.aw);
     const T *__restrict__ gout = static_cast<const T *>(a.gout);
     float *__restrict__ gimg = static_cast<float *>(a.gimg);
     T *__restrict__ gpts = static_cast<T *>(a.gpts);
@@ -69,19 +70,20 @@ __global__ void __launch_bounds__(THREADS, 1)
     if (tile >= t_end) continue;
 
     TileUnit tu = decode_tile(tile, tiles_per_bh, g, G, a);
-    float xy[2 * PPL], wa[PPL], go[VEC];
-    load_vec_stream<T, 2 * PPL>(pts + ((size_t)tu.u * LK + j * PPL) * 2, xy);
-    load_vec_stream<T, PPL>(aw + (size_t)tu.u * LK + j * PPL, wa);
+    LaneOperands<T, PPL, FUSED> op;
+    float go[VEC];
+    load_operands<T, LANES, LK, FUSED>(a, tu, j, op);
     load_vec_stream<T, VEC>(gout + (size_t)tu.u * a.D + j * VEC, go);
 
     for (; tile < t_end; tile += nwarps) {
         const int tile_n = tile + nwarps;
         const bool has_next = tile_n < t_end;
         const TileUnit tu_n = decode_tile(has_next ? tile_n : tile, tiles_per_bh, g, G, a);
-        float xy_n[2 * PPL], wa_n[PPL], go_n[VEC];
-        load_vec_stream<T, 2 * PPL>(pts + ((size_t)tu_n.u * LK + j * PPL) * 2, xy_n);
-        load_vec_stream<T, PPL>(aw + (size_t)tu_n.u * LK + j * PPL, wa_n);
+        LaneOperands<T, PPL, FUSED> op_n;
+        float go_n[VEC];
+        load_operands<T, LANES, LK, FUSED>(a, tu_n, j, op_n);
         load_vec_stream<T, VEC>(gout + (size_t)tu_n.u * a.D + j * VEC, go_n);
+        if constexpr (FUSED) derive_operands<T, LANES, LK>(a, s_lv, j, op);
 
         const unsigned char *__restrict__ lane_base =
             reinterpret_cast<const unsigned char *>(img + tu.bh_off + j * VEC);
@@ -94,7 +96,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll
         for (int pp = 0; pp < PPL; ++pp) {
             const Level lv = s_lv[(j * PPL + pp) / a.K];
-            tap[pp] = resolve_tap<BORDER>(xy[2 * pp], xy[2 * pp + 1], lv, align, row_bytes);
+            tap[pp] = resolve_tap<BORDER>(op.xy[2 * pp], op.xy[2 * pp + 1], lv, align, row_bytes);
             sx[pp] = align ? (float)(lv.w - 1) : (float)lv.w;
             sy[pp] = align ? (float)(lv.h - 1) : (float)lv.h;
         }
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                     const unsigned pack = __shfl_sync(0xffffffffu, tap[pp].pack, src, LANES);
                     fx[n] = __shfl_sync(0xffffffffu, tap[pp].dx, src, LANES);
                     fy[n] = __shfl_sync(0xffffffffu, tap[pp].dy, src, LANES);
-                    fw[n] = __shfl_sync(0xffffffffu, wa[pp], src, LANES) * live_scale;
+                    fw[n] = __shfl_sync(0xffffffffu, op.wa[pp], src, LANES) * live_scale;
                     corner_offsets(off, pack, row_bytes, o[n]);
                     msk[n] = BORDER ? 0xFu : ((pack >> kPackMaskShift) & 0xFu);
                     // always in range (clamped rows); zeros padding is applied to the dot products below
@@ -161,29 +163,92 @@ __global__ void __launch_bounds__(THREADS, 1)
         // ---- reduce over the LANES lanes; lane j ends with points [j*PPL, (j+1)*PPL) in part[0 .. 3*PPL) ----
         transpose_reduce<3 * LK, LANES / 2>(part, j);
 
-        if (tu.live) {
-            if (need_aw) {
-                float gw[PPL];
+        if constexpr (!FUSED) {
+            if (tu.live) {
+                if (need_aw) {
+                    float gw[PPL];
 #pragma unroll
-                for (int pp = 0; pp < PPL; ++pp) gw[pp] = part[3 * pp + 0];
-                store_vec_stream<T, PPL>(gaw + (size_t)tu.u * LK + j * PPL, gw);
-            }
-            if (need_pts) {
-                float gp[2 * PPL];
-#pragma unroll
-                for (int pp = 0; pp < PPL; ++pp) {
-                    gp[2 * pp + 0] = part[3 * pp + 1] * (wa[pp] * sx[pp]);
-                    gp[2 * pp + 1] = part[3 * pp + 2] * (wa[pp] * sy[pp]);
+                    for (int pp = 0; pp < PPL; ++pp) gw[pp] = part[3 * pp + 0];
+                    store_vec_stream<T, PPL>(gaw + (size_t)tu.u * LK + j * PPL, gw);
                 }
-                store_vec_stream<T, 2 * PPL>(gpts + ((size_t)tu.u * LK + j * PPL) * 2, gp);
+                if (need_pts) {
+                    float gp[2 * PPL];
+#pragma unroll
+                    for (int pp = 0; pp < PPL; ++pp) {
+                        gp[2 * pp + 0] = part[3 * pp + 1] * (op.wa[pp] * sx[pp]);
+                        gp[2 * pp + 1] = part[3 * pp + 2] * (op.wa[pp] * sy[pp]);
+                    }
+                    store_vec_stream<T, 2 * PPL>(gpts + ((size_t)tu.u * LK + j * PPL) * 2, gp);
+                }
+            }
+        } else {
+            // ---- module-core epilogue (frontend.py:253-284 differentiated) ----
+            //   logit:  g = w * (gw - sum_p w_p gw_p)                                  (softmax backward)
+            //   offset: 2-d ref: g = gpoint / (h | w of the level);  4-d ref: g = gpoint * ref_wh / (2K)
+            //   ref:    2-d: sum_p gpoint;  4-d: additionally sum_p gpoint * offset / (2K) for (w, h)
+            float gx[PPL], gy[PPL], dot = 0.0f;
+#pragma unroll
+            for (int pp = 0; pp < PPL; ++pp) {
+                gx[pp] = part[3 * pp + 1] * (op.wa[pp] * sx[pp]);
+                gy[pp] = part[3 * pp + 2] * (op.wa[pp] * sy[pp]);
+                dot = fmaf(op.wa[pp], part[3 * pp + 0], dot);
+            }
+            float r0 = 0.0f, r1 = 0.0f, r2 = 0.0f, r3 = 0.0f;
+            const float inv_2k = 1.0f / (float)(2 * a.K);
+#pragma unroll
+            for (int pp = 0; pp < PPL; ++pp) {
+                r0 += gx[pp];
+                r1 += gy[pp];
+                r2 = fmaf(gx[pp], op.raw[3 * pp + 0] * inv_2k, r2);
+                r3 = fmaf(gy[pp], op.raw[3 * pp + 1] * inv_2k, r3);
+            }
+#pragma unroll
+            for (int s = LANES / 2; s > 0; s >>= 1) {
+                dot += __shfl_xor_sync(0xffffffffu, dot, s);
+                r0 += __shfl_xor_sync(0xffffffffu, r0, s);
+                r1 += __shfl_xor_sync(0xffffffffu, r1, s);
+                r2 += __shfl_xor_sync(0xffffffffu, r2, s);
+                r3 += __shfl_xor_sync(0xffffffffu, r3, s);
+            }
+            if (tu.live) {
+                if (need_pts || need_aw) {
+                    float gtriple[3 * PPL];
+#pragma unroll
+                    for (int pp = 0; pp < PPL; ++pp) {
+                        const Level lv = s_lv[(j * PPL + pp) / a.K];
+                        if (a.ref_dim == 2) {
+                            gtriple[3 * pp + 0] = gx[pp] / (float)lv.h;
+                            gtriple[3 * pp + 1] = gy[pp] / (float)lv.w;
+                        } else {
+                            gtriple[3 * pp + 0] = gx[pp] * (op.ref[2] * inv_2k);
+                            gtriple[3 * pp + 1] = gy[pp] * (op.ref[3] * inv_2k);
+                        }
+                        gtriple[3 * pp + 2] = op.wa[pp] * (part[3 * pp + 0] - dot);
+                    }
+                    constexpr int E8 = 8 / (int)sizeof(T);
+                    T *__restrict__ gproj = static_cast<T *>(a.gproj) + ((size_t)tu.u * LK + j * PPL) * 3;
+#pragma unroll
+                    for (int c = 0; c < 3 * PPL / E8; ++c) {
+                        float tmp[E8];
+#pragma unroll
+                        for (int e = 0; e < E8; ++e) tmp[e] = gtriple[c * E8 + e];
+                        store_vec_stream<T, E8>(gproj + c * E8, tmp);
+                    }
+                }
+                if ((a.flags & kNeedRef) && j == 0) {
+                    float *gr = a.gref + (size_t)(tu.u / a.H) * a.ref_dim;
+                    red_add_v1(gr + 0, r0);
+                    red_add_v1(gr + 1, r1);
+                    if (a.ref_dim == 4) {
+                        red_add_v1(gr + 2, r2);
+                        red_add_v1(gr + 3, r3);
+                    }
+                }
             }
         }
 
         tu = tu_n;
-#pragma unroll
-        for (int i = 0; i < 2 * PPL; ++i) xy[i] = xy_n[i];
-#pragma unroll
-        for (int i = 0; i < PPL; ++i) wa[i] = wa_n[i];
+        op = op_n;
 #pragma unroll
         for (int i = 0; i < VEC; ++i) go[i] = go_n[i];
     }
@@ -191,7 +256,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 }
 
 
-template <typename T, int LANES, int LK>
+template <typename T, int LANES, int LK, bool FUSED = false>
 static cudaError_t launch_tiled_t(const KernelArgs &a, int sm_count, cudaStream_t st) {
     constexpr int THREADS = 512, NB = 2;
     constexpr int G = TiledCfg<T, LANES, LK>::G;
@@ -205,10 +270,19 @@ static cudaError_t launch_tiled_t(const KernelArgs &a, int sm_count, cudaStream_
     const size_t per_slice_factor = (a.flags & kNeedImg) ? sizeof(T) + sizeof(float) : sizeof(T);
     const WaveSchedule ws = make_wave_schedule(a, tiles_per_bh, per_slice_factor, kBwdL2Budget);
     if (a.border)
-        msda_bwd_tiled_kernel<T, LANES, LK, true, NB, THREADS><<<grid, THREADS, 0, st>>>(a, ws);
+        msda_bwd_tiled_kernel<T, LANES, LK, true, NB, THREADS, FUSED><<<grid, THREADS, 0, st>>>(a, ws);
     else
-        msda_bwd_tiled_kernel<T, LANES, LK, false, NB, THREADS><<<grid, THREADS, 0, st>>>(a, ws);
+        msda_bwd_tiled_kernel<T, LANES, LK, false, NB, THREADS, FUSED><<<grid, THREADS, 0, st>>>(a, ws);
     return cudaGetLastError();
+}
+
+// Backward of the fused module core; same eligibility as launch_module_forward_tiled.
+cudaError_t launch_module_backward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st) {
+    if (a.LK != 16 || a.L > 16 || a.D != 32 || (a.ref_dim != 2 && a.ref_dim != 4)) return cudaErrorNotSupported;
+    if (dtype == 0) return launch_tiled_t<float, 8, 16, true>(a, sm_count, st);
+    if (dtype == 1) return launch_tiled_t<__half, 4, 16, true>(a, sm_count, st);
+    if (dtype == 2) return launch_tiled_t<__nv_bfloat16, 4, 16, true>(a, sm_count, st);
+    return cudaErrorNotSupported;
 }
 
 // MSDA_B200_BWD_SPLIT=1 selects the experimental split backward: K1 = this file's kernel without grad_img, K2 =

@@ -27,6 +27,12 @@ struct KernelArgs {
     void *gimg;                // bwd: accumulation image (float for f32/f16/bf16 storage, double for f64)
     void *gpts;                // bwd: [B, Q, H, L, K, 2]
     void *gaw;                 // bwd: [B, Q, H, L, K]
+    // fused module core (frontend.py:253-289): raw projection + reference points instead of pts / aw
+    const void *proj;          // [B, Q, H, L, K, 3]  (offset x, offset y, attention logit)
+    const void *ref;           // [B, Q, ref_dim]     reference points, ref_dim = 2 (x,y) or 4 (cx,cy,w,h)
+    void *gproj;               // bwd: [B, Q, H, L, K, 3]
+    float *gref;               // bwd: [B, Q, ref_dim] fp32, zero-filled by the library, accumulated with atomics
+    int ref_dim;
     long long units;           // B*Q*H  (one unit = one output row (b,q,h))
     int B, Q, H, D, L, K, Npix;
     int LK;                    // L*K

@@ -12,7 +12,10 @@ namespace msda {
 // pyramid bytes of the slices gathered concurrently (one wave) -- well inside the 126 MB L2
 constexpr size_t kFwdL2Budget = 24u << 20;
 
-template <typename T, int LANES, int LK, bool BORDER, int NB, int THREADS>
+// FUSED = the module core (frontend.py:253-289): operands are the raw query projection [.., L, K, 3] and the reference
+// points; softmax and the sampling-point arithmetic happen in registers, sampling_points / attention_weights are never
+// materialised.
+template <typename T, int LANES, int LK, bool BORDER, int NB, int THREADS, bool FUSED>
 __global__ void __launch_bounds__(THREADS, 1)
     msda_fwd_tiled_kernel(const KernelArgs a, const WaveSchedule ws) {
     using Cfg = TiledCfg<T, LANES, LK>;
@@ -23,8 +26,6 @@ __global__ void __launch_bounds__(THREADS, 1)
     build_level_table(s_lv, a.shapes, a.L);
 
     const T *__restrict__ img = static_cast<const T *>(a.img);
-    const T *__restrict__ pts = static_cast<const T *>(a.pts);
-    const T *__restrict__ aw = static_cast<const T *>(a.aw);
     T *__restrict__ out = static_cast<T *>(a.out);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = THREADS >> 5;
@@ -42,17 +43,16 @@ __global__ void __launch_bounds__(THREADS, 1)
 
     // software pipeline: sampling points / weights of the next warp tile are in flight while this one is processed
     TileUnit tu = decode_tile(tile, tiles_per_bh, g, G, a);
-    float xy[2 * PPL], wa[PPL];
-    load_vec_stream<T, 2 * PPL>(pts + ((size_t)tu.u * LK + j * PPL) * 2, xy);
-    load_vec_stream<T, PPL>(aw + (size_t)tu.u * LK + j * PPL, wa);
+    LaneOperands<T, PPL, FUSED> op;
+    load_operands<T, LANES, LK, FUSED>(a, tu, j, op);
 
     for (; tile < t_end; tile += nwarps) {
         const int tile_n = tile + nwarps;
         const bool has_next = tile_n < t_end;
         const TileUnit tu_n = decode_tile(has_next ? tile_n : tile, tiles_per_bh, g, G, a);
-        float xy_n[2 * PPL], wa_n[PPL];
-        load_vec_stream<T, 2 * PPL>(pts + ((size_t)tu_n.u * LK + j * PPL) * 2, xy_n);
-        load_vec_stream<T, PPL>(aw + (size_t)tu_n.u * LK + j * PPL, wa_n);
+        LaneOperands<T, PPL, FUSED> op_n;
+        load_operands<T, LANES, LK, FUSED>(a, tu_n, j, op_n);
+        if constexpr (FUSED) derive_operands<T, LANES, LK>(a, s_lv, j, op);
 
         const unsigned char *__restrict__ lane_base =
             reinterpret_cast<const unsigned char *>(img + tu.bh_off + j * VEC);
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         TileTap tap[PPL];
 #pragma unroll
         for (int pp = 0; pp < PPL; ++pp)
-            tap[pp] = resolve_tap<BORDER>(xy[2 * pp], xy[2 * pp + 1], s_lv[(j * PPL + pp) / a.K], align, row_bytes);
+            tap[pp] = resolve_tap<BORDER>(op.xy[2 * pp], op.xy[2 * pp + 1], s_lv[(j * PPL + pp) / a.K], align, row_bytes);
 
         float acc[VEC];
 #pragma unroll
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                     const unsigned pack = __shfl_sync(0xffffffffu, tap[pp].pack, src, LANES);
                     fx[n] = __shfl_sync(0xffffffffu, tap[pp].dx, src, LANES);
                     fy[n] = __shfl_sync(0xffffffffu, tap[pp].dy, src, LANES);
-                    fw[n] = __shfl_sync(0xffffffffu, wa[pp], src, LANES);
+                    fw[n] = __shfl_sync(0xffffffffu, op.wa[pp], src, LANES);
                     msk[n] = (pack >> kPackMaskShift) & 0xFu;
                     unsigned o[4];
                     corner_offsets(off, pack, row_bytes, o);
@@ -113,15 +113,12 @@ __global__ void __launch_bounds__(THREADS, 1)
         if (tu.live) store_vec_stream<T, VEC>(out + (size_t)tu.u * a.D + j * VEC, acc);
 
         tu = tu_n;
-#pragma unroll
-        for (int i = 0; i < 2 * PPL; ++i) xy[i] = xy_n[i];
-#pragma unroll
-        for (int i = 0; i < PPL; ++i) wa[i] = wa_n[i];
+        op = op_n;
     }
     }  // waves
 }
 
-template <typename T, int LANES, int LK, int THREADS, int NB>
+template <typename T, int LANES, int LK, int THREADS, int NB, bool FUSED = false>
 static cudaError_t launch_tiled_cfg(const KernelArgs &a, int sm_count, cudaStream_t st) {
     constexpr int G = TiledCfg<T, LANES, LK>::G;
     if (!tiled_offsets_fit(a, sizeof(T))) return cudaErrorNotSupported;
@@ -132,9 +129,9 @@ static cudaError_t launch_tiled_cfg(const KernelArgs &a, int sm_count, cudaStrea
     const int grid = (int)(want < sm_count ? (want < 1 ? 1 : want) : sm_count);
     const WaveSchedule ws = make_wave_schedule(a, tiles_per_bh, sizeof(T), kFwdL2Budget);
     if (a.border)
-        msda_fwd_tiled_kernel<T, LANES, LK, true, NB, THREADS><<<grid, THREADS, 0, st>>>(a, ws);
+        msda_fwd_tiled_kernel<T, LANES, LK, true, NB, THREADS, FUSED><<<grid, THREADS, 0, st>>>(a, ws);
     else
-        msda_fwd_tiled_kernel<T, LANES, LK, false, NB, THREADS><<<grid, THREADS, 0, st>>>(a, ws);
+        msda_fwd_tiled_kernel<T, LANES, LK, false, NB, THREADS, FUSED><<<grid, THREADS, 0, st>>>(a, ws);
     return cudaGetLastError();
 }
 
@@ -164,6 +161,15 @@ cudaError_t launch_forward_tiled(const KernelArgs &a, int dtype, int sm_count, c
         if (a.D == 32) return launch_tiled_t<__nv_bfloat16, 4, 16>(a, sm_count, st);
         if (a.D == 64) return launch_tiled_t<__nv_bfloat16, 8, 16>(a, sm_count, st);
     }
+    return cudaErrorNotSupported;
+}
+
+// Fused module core: (fp32 | fp16 | bf16) x D=32 x L*K=16 -- hidden 256 / 8 heads, the Deformable-DETR family.
+cudaError_t launch_module_forward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st) {
+    if (a.LK != 16 || a.L > 16 || a.D != 32 || (a.ref_dim != 2 && a.ref_dim != 4)) return cudaErrorNotSupported;
+    if (dtype == 0) return launch_tiled_cfg<float, 8, 16, 1024, 2, true>(a, sm_count, st);
+    if (dtype == 1) return launch_tiled_cfg<__half, 4, 16, 512, 4, true>(a, sm_count, st);
+    if (dtype == 2) return launch_tiled_cfg<__nv_bfloat16, 4, 16, 512, 4, true>(a, sm_count, st);
     return cudaErrorNotSupported;
 }
 

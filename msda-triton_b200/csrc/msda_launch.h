@@ -15,6 +15,11 @@ cudaError_t launch_backward_generic(const KernelArgs &a, int dtype, int vec, int
 cudaError_t launch_forward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st);
 cudaError_t launch_backward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st);
 
+// Fused module core (raw projection + reference points in, see msda_tiled.cuh).  cudaErrorNotSupported when the
+// problem is outside (fp32|fp16|bf16) x D=32 x L*K=16.
+cudaError_t launch_module_forward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st);
+cudaError_t launch_module_backward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st);
+
 // grad_img alone, without gathers (split backward; msda_bwd_scatter.cu).  a.gimg = zero-filled fp32 accumulation image.
 cudaError_t launch_backward_scatter(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st);
 

@@ -131,6 +131,92 @@ __device__ __forceinline__ void corner_offsets(unsigned off, unsigned pack, unsi
     o[3] = off + sy + sx;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Per-lane operands of one unit: either the materialised sampling points / attention weights (the operator of
+// frontend.py:145) or, for the fused module core, the raw query projection and the reference point, from which the
+// lane group derives them on the fly (frontend.py:253-284: softmax over L*K, ref + offset / level shape).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kNeedRef = 16;   // msda_module_backward: grad of the reference points requested
+
+template <typename T, int PPL, bool FUSED> struct LaneOperands {
+    float xy[2 * PPL];    // sampling points of this lane's PPL points (x, y)
+    float wa[PPL];        // attention weights
+    float raw[FUSED ? 3 * PPL : 1];   // FUSED: (offset x, offset y, logit) triples as loaded
+    float ref[FUSED ? 4 : 1];         // FUSED: reference point of the unit's query
+};
+
+// Issues the (streaming) loads for unit `tu` -- nothing here depends on the loaded values, so the call can sit one
+// warp tile ahead of its use.
+template <typename T, int LANES, int LK, bool FUSED>
+__device__ __forceinline__ void load_operands(const KernelArgs &a, const TileUnit &tu, int j,
+                                              LaneOperands<T, LK / LANES, FUSED> &op) {
+    constexpr int PPL = LK / LANES;
+    if constexpr (!FUSED) {
+        const T *__restrict__ pts = static_cast<const T *>(a.pts);
+        const T *__restrict__ aw = static_cast<const T *>(a.aw);
+        load_vec_stream<T, 2 * PPL>(pts + ((size_t)tu.u * LK + j * PPL) * 2, op.xy);
+        load_vec_stream<T, PPL>(aw + (size_t)tu.u * LK + j * PPL, op.wa);
+    } else {
+        constexpr int E8 = 8 / (int)sizeof(T);            // elements per 8-byte chunk
+        static_assert((3 * PPL) % E8 == 0, "fused operands are fetched in 8-byte chunks");
+        const T *__restrict__ proj = static_cast<const T *>(a.proj) + ((size_t)tu.u * LK + j * PPL) * 3;
+#pragma unroll
+        for (int c = 0; c < 3 * PPL / E8; ++c) {
+            float tmp[E8];
+            load_vec_stream<T, E8>(proj + c * E8, tmp);
+#pragma unroll
+            for (int e = 0; e < E8; ++e) op.raw[c * E8 + e] = tmp[e];
+        }
+        const T *__restrict__ ref = static_cast<const T *>(a.ref) + (size_t)(tu.u / a.H) * a.ref_dim;
+        float r2[2];
+        load_vec<T, 2>(ref, r2);
+        op.ref[0] = r2[0];
+        op.ref[1] = r2[1];
+        op.ref[2] = op.ref[3] = 0.0f;
+        if (a.ref_dim == 4) {
+            load_vec<T, 2>(ref + 2, r2);
+            op.ref[2] = r2[0];
+            op.ref[3] = r2[1];
+        }
+    }
+}
+
+// FUSED only: turns (raw, ref) into (xy, wa).  Softmax runs over the LK logits of the unit, which are spread over the
+// LANES lanes of the group (PPL each): two butterfly reductions.  Same arithmetic order as the torch module in fp32:
+// exp(x - max) / sum;  ref + off / shape  (x is divided by the level HEIGHT and y by the WIDTH, as the reference
+// does, frontend.py:272-276);  ref_xy + off * ref_wh / (2 K)  for 4-d reference points (frontend.py:278-282).
+template <typename T, int LANES, int LK>
+__device__ __forceinline__ void derive_operands(const KernelArgs &a, const Level *s_lv, int j,
+                                                LaneOperands<T, LK / LANES, true> &op) {
+    constexpr int PPL = LK / LANES;
+    float m = op.raw[2];
+#pragma unroll
+    for (int pp = 1; pp < PPL; ++pp) m = fmaxf(m, op.raw[3 * pp + 2]);
+#pragma unroll
+    for (int s = LANES / 2; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+    float sum = 0.0f;
+#pragma unroll
+    for (int pp = 0; pp < PPL; ++pp) {
+        op.wa[pp] = expf(op.raw[3 * pp + 2] - m);
+        sum += op.wa[pp];
+    }
+#pragma unroll
+    for (int s = LANES / 2; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+#pragma unroll
+    for (int pp = 0; pp < PPL; ++pp) {
+        op.wa[pp] = __fdiv_rn(op.wa[pp], sum);
+        const Level lv = s_lv[(j * PPL + pp) / a.K];
+        if (a.ref_dim == 2) {
+            op.xy[2 * pp + 0] = op.ref[0] + __fdiv_rn(op.raw[3 * pp + 0], (float)lv.h);
+            op.xy[2 * pp + 1] = op.ref[1] + __fdiv_rn(op.raw[3 * pp + 1], (float)lv.w);
+        } else {
+            const float two_k = (float)(2 * a.K);
+            op.xy[2 * pp + 0] = op.ref[0] + __fdiv_rn(__fmul_rn(op.raw[3 * pp + 0], op.ref[2]), two_k);
+            op.xy[2 * pp + 1] = op.ref[1] + __fdiv_rn(__fmul_rn(op.raw[3 * pp + 1], op.ref[3]), two_k);
+        }
+    }
+}
+
 // 128-bit read-only gather of one corner row slice (VEC storage elements, kept raw until they are consumed).
 __device__ __forceinline__ uint4 gather_row(const unsigned char *__restrict__ lane_base, unsigned byte_off) {
     return __ldg(reinterpret_cast<const uint4 *>(lane_base + byte_off));

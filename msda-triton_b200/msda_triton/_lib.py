@@ -16,7 +16,7 @@ ABI_VERSION = 1
 
 DTYPE_F32, DTYPE_F16, DTYPE_BF16, DTYPE_F64 = 0, 1, 2, 3
 PAD_ZEROS, PAD_BORDER = 0, 1
-BWD_NEED_IMG, BWD_NEED_POINTS, BWD_NEED_WEIGHTS, BWD_DETERMINISTIC = 1, 2, 4, 8
+BWD_NEED_IMG, BWD_NEED_POINTS, BWD_NEED_WEIGHTS, BWD_DETERMINISTIC, BWD_NEED_REF = 1, 2, 4, 8, 16
 
 
 class MsdaProblem(ctypes.Structure):
@@ -48,6 +48,12 @@ def _load() -> ctypes.CDLL:
     lib.msda_backward_workspace_bytes.argtypes = [pp, ci]
     lib.msda_backward.restype = ci
     lib.msda_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, pp, ci, vp, sz, vp]
+    lib.msda_module_supported.restype = ci
+    lib.msda_module_supported.argtypes = [pp, ci]
+    lib.msda_module_forward.restype = ci
+    lib.msda_module_forward.argtypes = [vp, vp, vp, vp, vp, ci, pp, vp]
+    lib.msda_module_backward.restype = ci
+    lib.msda_module_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ci, pp, ci, vp, sz, vp]
     lib.msda_level_table.restype = ci
     lib.msda_level_table.argtypes = [vp, vp, i64, i64, vp]
     lib.msda_probe_gather.restype = ci

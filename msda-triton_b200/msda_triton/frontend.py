@@ -15,6 +15,7 @@ run the torch route the reference documents for ``device="cpu"`` (README.md:132)
 """
 from __future__ import annotations
 
+import os
 from typing import Literal
 
 import torch
@@ -26,6 +27,10 @@ from torch.autograd.function import once_differentiable
 from . import kernels
 
 PaddingMode = Literal["border", "zeros"]
+
+
+def _fused_module_enabled() -> bool:
+    return os.environ.get("MSDA_B200_FUSED_MODULE", "1") != "0"
 
 # dtypes of the CUDA route: the reference's three (frontend.py:84) plus bf16, which its Triton helper rejects
 # (kernels.py:40-41) and therefore sends down the torch route.
@@ -94,6 +99,38 @@ class _B200MsdaFunction(torch.autograd.Function):
             out_grad, img, img_shapes, sampling_points, attention_weights, ctx.padding_mode, ctx.align_corners,
             needs=needs)
         return img_grad, None, points_grad, weights_grad, None, None
+
+
+class _B200ModuleCoreFunction(torch.autograd.Function):
+    """The module's core between its projections (frontend.py:253-289 of the reference) as ONE kernel each way:
+    softmax over L*K, sampling-point arithmetic and the MSDA operator, without materialising sampling_points /
+    attention_weights.  Same AMP contract as the operator (fp32 under autocast)."""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, value, img_shapes, projection, reference_points, padding_mode, align_corners):
+        ctx.save_for_backward(value, img_shapes, projection, reference_points)
+        ctx.padding_mode = padding_mode
+        ctx.align_corners = align_corners
+        return kernels.b200_module_core_fwd(value, img_shapes, projection, reference_points, padding_mode, align_corners)
+
+    @staticmethod
+    @once_differentiable
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, out_grad):
+        value, img_shapes, projection, reference_points = ctx.saved_tensors
+        needs = (ctx.needs_input_grad[0], ctx.needs_input_grad[2], ctx.needs_input_grad[3])
+        gvalue, gproj, gref = kernels.b200_module_core_bwd(
+            out_grad, value, img_shapes, projection, reference_points, ctx.padding_mode, ctx.align_corners, needs=needs)
+        return gvalue, None, gproj, gref, None, None
+
+
+def fused_module_core(value, img_shapes, projection, reference_points, padding_mode: PaddingMode,
+                      align_corners: bool) -> torch.Tensor:
+    """``projection`` is the query projection viewed as ``[B, N, H, L, P, 3]`` (offset x, offset y, attention logit),
+    ``value`` the projected pyramid ``[B, I, H, C]``; returns ``[B, N, H, C]``."""
+    return _B200ModuleCoreFunction.apply(value, img_shapes, projection, reference_points, padding_mode,
+                                         bool(align_corners))
 
 
 def b200_multiscale_deformable_attention(
@@ -239,11 +276,24 @@ class MultiscaleDeformableAttention(nn.Module):
 
         # offsets and logits come out of ONE projection, interleaved as (..., point, 3) (frontend.py:253-257)
         projected = self.query_input_proj(queries).reshape(batch, num_queries, heads, levels, points, 3)
+        value = self.img_input_proj(img).reshape(batch, num_pixels, heads, self.hidden_dim // heads)
+        if reference_points.shape[-1] not in (2, 4):
+            raise ValueError(
+                f"`reference_points` should have the last dim either 2 or 4, but got {reference_points.shape[-1]}.")
+
+        # CUDA fast path: softmax, sampling-point arithmetic and the operator in one kernel (no materialised
+        # sampling_points / attention_weights).  Set MSDA_B200_FUSED_MODULE=0 to take the composed path below.
+        if value.is_cuda and _fused_module_enabled() and not torch.compiler.is_compiling():
+            ref = reference_points.to(value.dtype)
+            if img_shapes.device != value.device:
+                img_shapes = img_shapes.to(value.device, non_blocking=True)
+            if kernels.module_core_supported(value, projected, ref):
+                out = fused_module_core(value, img_shapes, projected, ref, self.padding_mode, self.align_corners)
+                return self.query_output_proj(out.reshape(batch, num_queries, self.hidden_dim))
+
         offsets, logits = projected[..., :2], projected[..., 2]
         attention_weights = logits.reshape(batch, num_queries, heads, levels * points).softmax(dim=-1)
         attention_weights = attention_weights.reshape(batch, num_queries, heads, levels, points)
-
-        value = self.img_input_proj(img).reshape(batch, num_pixels, heads, self.hidden_dim // heads)
 
         anchor = reference_points[:, :, None, None, None, :]
         coords = reference_points.shape[-1]
@@ -253,8 +303,6 @@ class MultiscaleDeformableAttention(nn.Module):
             sampling_points = anchor + offsets / img_shapes[:, None, :]
         elif coords == 4:
             sampling_points = anchor[..., :2] + offsets * anchor[..., 2:] / (2 * points)
-        else:
-            raise ValueError(f"`reference_points` should have the last dim either 2 or 4, but got {coords}.")
 
         out = multiscale_deformable_attention(
             value, img_shapes, sampling_points, attention_weights, self.padding_mode, self.align_corners)

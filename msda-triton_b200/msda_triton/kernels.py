@@ -139,6 +139,74 @@ def b200_multi_scale_deformable_attention_bwd(
     return gimg, gpts, gaw
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# fused module core (frontend.py:253-289 of the reference in one kernel)
+# ---------------------------------------------------------------------------------------------------------------------
+def _module_problem(value, img_shapes, proj, ref, padding_mode, align_corners) -> _lib.MsdaProblem:
+    if padding_mode not in _PAD_CODE:
+        raise ValueError(f"`padding_mode` should be 'border' or 'zeros', but got {padding_mode!r}.")
+    B, Npix, H, D = value.shape
+    B2, Q, H2, L, K, three = proj.shape
+    if three != 3 or B2 != B or H2 != H or tuple(img_shapes.shape) != (L, 2) or ref.shape[:2] != (B, Q) \
+            or ref.shape[-1] not in (2, 4):
+        raise ValueError(
+            f"Inconsistent shapes: value {tuple(value.shape)}, img_shapes {tuple(img_shapes.shape)}, "
+            f"projection {tuple(proj.shape)}, reference_points {tuple(ref.shape)}.")
+    if not (value.dtype == proj.dtype == ref.dtype) or value.dtype not in _DTYPE_CODE:
+        raise ValueError("value / projection / reference_points must share one dtype.")
+    return _lib.MsdaProblem(B, Npix, H, D, Q, L, K, _DTYPE_CODE[value.dtype], _PAD_CODE[padding_mode],
+                            int(bool(align_corners)), 0)
+
+
+def module_core_supported(value: torch.Tensor, proj: torch.Tensor, ref: torch.Tensor) -> bool:
+    """True when the fused kernels cover this problem (CUDA, fp32/fp16/bf16, head_dim 32, L*K == 16)."""
+    if not value.is_cuda or value.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+        return False
+    if not (value.dtype == proj.dtype == ref.dtype) or proj.dim() != 6 or ref.shape[-1] not in (2, 4):
+        return False
+    B, Npix, H, D = value.shape
+    _, Q, _, L, K, _ = proj.shape
+    prob = _lib.MsdaProblem(B, Npix, H, D, Q, L, K, _DTYPE_CODE[value.dtype], 0, 0, 0)
+    return bool(_lib.get_lib().msda_module_supported(ctypes.byref(prob), int(ref.shape[-1])))
+
+
+def b200_module_core_fwd(value, img_shapes, proj, ref, padding_mode, align_corners) -> torch.Tensor:
+    """out = MSDA(value, softmax / sampling-point arithmetic of (proj, ref)) without materialising the operands."""
+    value, proj, ref = _dense(value), _dense(proj), _dense(ref)
+    shapes = _shapes_i64(img_shapes)
+    prob = _module_problem(value, shapes, proj, ref, padding_mode, align_corners)
+    out = torch.empty((prob.B, prob.Q, prob.H, prob.D), dtype=value.dtype, device=value.device)
+    with torch.cuda.device_of(value):
+        rc = _lib.get_lib().msda_module_forward(_ptr(out), _ptr(value), _ptr(shapes), _ptr(proj), _ptr(ref),
+                                                int(ref.shape[-1]), ctypes.byref(prob), _stream_ptr())
+    _lib.check(rc, "msda_module_forward")
+    return out
+
+
+def b200_module_core_bwd(out_grad, value, img_shapes, proj, ref, padding_mode, align_corners,
+                         needs: Sequence[bool] = (True, True, True)):
+    """Returns (grad_value, grad_proj, grad_ref); grad_ref comes back in the storage dtype."""
+    value, proj, ref = _dense(value), _dense(proj), _dense(ref)
+    shapes = _shapes_i64(img_shapes)
+    prob = _module_problem(value, shapes, proj, ref, padding_mode, align_corners)
+    gout = _dense(out_grad.to(value.dtype))
+    need_value, need_proj, need_ref = (bool(n) for n in needs)
+    flags = (_lib.BWD_NEED_IMG * need_value) | ((_lib.BWD_NEED_POINTS | _lib.BWD_NEED_WEIGHTS) * need_proj) \
+        | (_lib.BWD_NEED_REF * need_ref)
+    gvalue = torch.empty(value.shape, dtype=value.dtype, device=value.device) if need_value else None
+    gproj = torch.empty(proj.shape, dtype=proj.dtype, device=value.device) if need_proj else None
+    gref32 = torch.empty(ref.shape, dtype=torch.float32, device=value.device) if need_ref else None
+    with torch.cuda.device_of(value):
+        ws_bytes = int(_lib.get_lib().msda_backward_workspace_bytes(ctypes.byref(prob), flags & 7))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=value.device) if ws_bytes else None
+        rc = _lib.get_lib().msda_module_backward(
+            _ptr(gvalue), _ptr(gproj), _ptr(gref32), _ptr(gout), _ptr(value), _ptr(shapes), _ptr(proj), _ptr(ref),
+            int(ref.shape[-1]), ctypes.byref(prob), flags, _ptr(ws), ws_bytes, _stream_ptr())
+    _lib.check(rc, "msda_module_backward")
+    gref = gref32.to(ref.dtype) if need_ref else None
+    return gvalue, gproj, gref
+
+
 def level_table(img_shapes: torch.Tensor, num_pixels: int) -> torch.Tensor:
     """Device-side level preprocessing: int32 [L+1, 4] rows {h, w, offset, 0} + {sum, Npix, sum==Npix, 0}."""
     shapes = _shapes_i64(img_shapes)

@@ -1,0 +1,145 @@
+"""Fused module core (softmax + sampling-point arithmetic + MSDA in one kernel each way) against (a) the composed
+torch prologue + CPU route in fp64 and (b) the same nn.Module taking the composed CUDA path."""
+import itertools
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from util import BENCH_PYRAMID, DETR_PYRAMID, assert_close, to_np
+
+pytestmark = pytest.mark.gpu
+
+
+def composed_reference(value, shapes, proj, ref, pm, ac):
+    """frontend.py:253-289 of the reference, spelled out on CPU in fp64 with torch autograd."""
+    from msda_triton.frontend import native_multiscale_deformable_attention
+    B, Q, H, L, K, _ = proj.shape
+    off, logit = proj[..., :2], proj[..., 2]
+    aw = logit.reshape(B, Q, H, L * K).softmax(-1).reshape(B, Q, H, L, K)
+    anchor = ref[:, :, None, None, None, :]
+    if ref.shape[-1] == 2:
+        pts = anchor + off / shapes[:, None, :]
+    else:
+        pts = anchor[..., :2] + off * anchor[..., 2:] / (2 * K)
+    return native_multiscale_deformable_attention(value, shapes, pts, aw, pm, ac)
+
+
+@pytest.mark.parametrize("coords", [2, 4])
+@pytest.mark.parametrize("pm,ac", list(itertools.product(("zeros", "border"), (False, True))))
+@pytest.mark.parametrize("pyramid", [BENCH_PYRAMID, [(25, 42), (13, 21), (7, 11), (4, 6)]], ids=["square", "rect"])
+def test_fused_core_matches_composed_fp64(coords, pm, ac, pyramid):
+    from msda_triton.frontend import fused_module_core
+    g = torch.Generator().manual_seed(31 + coords)
+    B, Q, H, D, L, K = 2, 333, 8, 32, 4, 4
+    npix = sum(h * w for h, w in pyramid)
+    value = torch.randn(B, npix, H, D, generator=g)
+    proj = torch.randn(B, Q, H, L, K, 3, generator=g)
+    proj[..., :2] *= 3.0                                   # offsets of a few pixels
+    ref = torch.rand(B, Q, coords, generator=g)
+    if coords == 4:
+        ref[..., 2:] = ref[..., 2:] * 0.5 + 0.05
+    go = torch.rand(B, Q, H, D, generator=g)
+    shapes = torch.tensor(pyramid)
+
+    a, b, c = (t.double().requires_grad_(True) for t in (value, proj, ref))
+    want = composed_reference(a, shapes, b, c, pm, ac)
+    want.backward(go.double())
+
+    x, y, z = (t.cuda().requires_grad_(True) for t in (value, proj, ref))
+    got = fused_module_core(x, shapes.cuda(), y, z, pm, ac)
+    got.backward(go.cuda())
+    assert_close(to_np(got), to_np(want), 1e-4, 1e-5, "out")
+    for t, r, what in ((x.grad, a.grad, "grad_value"), (y.grad, b.grad, "grad_projection"), (z.grad, c.grad, "grad_ref")):
+        r = to_np(r)
+        assert_close(to_np(t), r, 1e-3, 2e-5 * np.abs(r).max(), what, max_outliers=4)
+
+
+@pytest.mark.parametrize("coords", [2, 4])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_module_fused_equals_composed_cuda(coords, dtype):
+    """Same module, same weights: fused fast path vs the composed CUDA path (MSDA_B200_FUSED_MODULE=0) run in fp32.
+    (For bf16 the composed path itself rounds the sampling points to bf16 -- a quarter of a pixel on a 64-pixel level --
+    so the yardstick is the fp32 composed module on the same bf16-rounded weights and inputs.)"""
+    import copy
+    from msda_triton import MultiscaleDeformableAttention
+    torch.manual_seed(3)
+    emb, heads, levels, points = 256, 8, 4, 4
+    npix = sum(h * w for h, w in BENCH_PYRAMID)
+    img = torch.randn(2, npix, emb).to("cuda", dtype)
+    queries = torch.randn(2, 200, emb).to("cuda", dtype)
+    ref_pts = (torch.rand(2, 200, coords) * 0.8 + 0.1).to("cuda", dtype)
+    shapes = torch.tensor(BENCH_PYRAMID, device="cuda")
+    module = MultiscaleDeformableAttention(emb, emb, levels, heads, points, "border", True).to("cuda", dtype)
+    reference = copy.deepcopy(module).float()
+
+    def run(mod, cast, fused):
+        os.environ["MSDA_B200_FUSED_MODULE"] = "1" if fused else "0"
+        try:
+            i, q, r = (t.to(cast).clone().requires_grad_(True) for t in (img, queries, ref_pts))
+            mod.zero_grad()
+            out = mod(i, shapes, q, r)
+            out.float().square().sum().backward()
+            return [out.detach(), i.grad, q.grad, r.grad] + [p.grad.clone() for p in mod.parameters()]
+        finally:
+            os.environ.pop("MSDA_B200_FUSED_MODULE")
+
+    got = run(module, dtype, fused=True)
+    want = run(reference, torch.float32, fused=False)
+    # Gradients that pass through the sampling OFFSETS are discontinuous at pixel boundaries, and bf16-quantised
+    # reference points / offsets land on such boundaries often (few mantissa bits): fp32 and fp64 evaluation then pick
+    # different cells for a small fraction of the points.  Hence: a tolerance for the bulk, plus an outlier budget.
+    rtol, atol, frac = (2e-4, 2e-4, 1e-4) if dtype == torch.float32 else (5e-2, 3e-2, 6e-2)
+    for a, b in zip(got, want):
+        b = to_np(b)
+        assert a.dtype == dtype
+        assert_close(to_np(a), b, rtol, atol * max(1e-3, np.abs(b).max()), "fused vs composed",
+                     max_outliers=max(8, int(frac * b.size)))
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+@pytest.mark.parametrize("coords", [2, 4])
+def test_fused_core_16bit_storage(dtype, coords):
+    """16-bit storage, fp32 compute: out and grad_value (continuous in the inputs) within one storage rounding of the
+    fp64 composed reference on the same rounded inputs; offset / reference gradients within the same bound except for
+    the boundary-tie outliers described above (< 2 % of the offset gradients; each reference-point gradient sums 128 of
+    them, so up to 10 % of those may contain one)."""
+    from msda_triton.frontend import fused_module_core
+    g = torch.Generator().manual_seed(5)
+    B, Q, H, D, L, K = 2, 333, 8, 32, 4, 4
+    npix = sum(h * w for h, w in BENCH_PYRAMID)
+    value = torch.randn(B, npix, H, D, generator=g).to(dtype)
+    proj = torch.randn(B, Q, H, L, K, 3, generator=g)
+    proj[..., :2] *= 3.0
+    proj = proj.to(dtype)
+    ref = torch.rand(B, Q, coords, generator=g).to(dtype)
+    go = torch.rand(B, Q, H, D, generator=g).to(dtype)
+    shapes = torch.tensor(BENCH_PYRAMID)
+    a, b, c = (t.double().requires_grad_(True) for t in (value, proj, ref))
+    want = composed_reference(a, shapes, b, c, "border", True)
+    want.backward(go.double())
+    x, y, z = (t.cuda().requires_grad_(True) for t in (value, proj, ref))
+    got = fused_module_core(x, shapes.cuda(), y, z, "border", True)
+    got.backward(go.cuda())
+    eps = 2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -10
+    for t, r, what, frac in ((got, want, "out", 0.0), (x.grad, a.grad, "grad_value", 0.0),
+                             (y.grad, b.grad, "grad_projection", 0.02), (z.grad, c.grad, "grad_ref", 0.10)):
+        r = to_np(r)
+        assert t.dtype == dtype
+        assert_close(to_np(t), r, eps, eps * 2e-2 * np.abs(r).max(), f"{dtype} {what}", max_outliers=int(frac * r.size))
+
+
+def test_fused_core_rejects_unsupported_and_falls_back():
+    from msda_triton import MultiscaleDeformableAttention, kernels
+    value = torch.randn(1, 85, 2, 4, device="cuda")           # head_dim 4: not covered by the fused kernels
+    proj = torch.randn(1, 5, 2, 4, 8, 3, device="cuda")
+    ref = torch.rand(1, 5, 2, device="cuda")
+    assert not kernels.module_core_supported(value, proj, ref)
+    with pytest.raises(ValueError):
+        kernels.b200_module_core_fwd(value, torch.tensor([(8, 8), (4, 4), (2, 2), (1, 1)], device="cuda"), proj, ref,
+                                     "zeros", False)
+    module = MultiscaleDeformableAttention(64, 8, 4, 2, 8, "border", True).cuda()      # falls back to the composed path
+    out = module(torch.randn(1, 85, 64, device="cuda"), torch.tensor([(8, 8), (4, 4), (2, 2), (1, 1)], device="cuda"),
+                 torch.randn(1, 5, 64, device="cuda"), ref)
+    assert out.shape == (1, 5, 64)
