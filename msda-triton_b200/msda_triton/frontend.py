@@ -283,7 +283,8 @@ class MultiscaleDeformableAttention(nn.Module):
 
         # CUDA fast path: softmax, sampling-point arithmetic and the operator in one kernel (no materialised
         # sampling_points / attention_weights).  Set MSDA_B200_FUSED_MODULE=0 to take the composed path below.
-        if value.is_cuda and _fused_module_enabled() and not torch.compiler.is_compiling():
+        if (value.is_cuda and _fused_module_enabled() and not torch.compiler.is_compiling()
+                and not kernels.is_deterministic()):   # the bit-reproducible grad_img lives on the composed path
             ref = reference_points.to(value.dtype)
             if img_shapes.device != value.device:
                 img_shapes = img_shapes.to(value.device, non_blocking=True)
