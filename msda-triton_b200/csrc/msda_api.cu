@@ -79,6 +79,7 @@ int validate(const msda_problem *p) {
     if (p->Npix > kInt || p->Q > kInt || p->H > kInt || p->D > kInt || p->B > kInt || p->L * p->K > (1 << 20) ||
         p->L > 2048)
         return fail(MSDA_ERR_BAD_SHAPE, "a dimension exceeds the supported range (each < 2^31, L <= 2048, L*K <= 2^20)");
+    if (p->B * p->H > kInt) return fail(MSDA_ERR_BAD_SHAPE, "B*H must be below 2^31");
     if (p->Npix * p->H * p->D > (1LL << 46))
         return fail(MSDA_ERR_BAD_SHAPE, "one image of the pyramid is too large");
     return MSDA_OK;
