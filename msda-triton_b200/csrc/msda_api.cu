@@ -282,11 +282,28 @@ int msda_backward(void *grad_img, void *grad_points, void *grad_weights, const v
                           aligned(attention_weights, 8) && aligned(grad_points, 16) && aligned(grad_weights, 8) &&
                           aligned(accum, 16);
     if (tiled_ok) e = msda::launch_backward_tiled(a, prob->dtype, dev.sm_count, st);
-    if (e == cudaErrorNotSupported) e = msda::launch_backward_generic(a, prob->dtype, vec, dev.sm_count, st);
+    if (e == cudaErrorNotSupported) {
+        // generic kernel, 16-bit storage: lanes of 4 channels make every red.v4 a whole, contiguous 16 bytes
+        if (staged && vec > 4) {
+            vec = 4;
+            fill_args(a, prob, vec);
+            a.img = img;
+            a.shapes = reinterpret_cast<const long long *>(img_shapes);
+            a.pts = sampling_points;
+            a.aw = attention_weights;
+            a.gout = grad_out;
+            a.gimg = accum;
+            a.gpts = grad_points;
+            a.gaw = grad_weights;
+            a.flags = flags & MSDA_BWD_NEED_ALL;
+        }
+        e = msda::launch_backward_generic(a, prob->dtype, vec, dev.sm_count, st);
+    }
     if (e != cudaSuccess) return fail_cuda(e, "msda_backward launch");
 
     if (staged) {
-        e = msda::launch_round_grad_img(grad_img, static_cast<const float *>(accum), (long long)img_elems, prob->dtype, st);
+        e = msda::launch_round_grad_img(grad_img, static_cast<const float *>(accum), (long long)img_elems, prob->dtype,
+                                        (int)prob->D, /*permuted_lanes=*/0, st);   // natural channel order on both paths
         if (e != cudaSuccess) return fail_cuda(e, "msda_backward grad_img rounding");
     }
     return MSDA_OK;
@@ -396,7 +413,8 @@ int msda_module_backward(void *grad_value, void *grad_proj, float *grad_ref, con
     e = msda::launch_module_backward_tiled(a, prob->dtype, dev.sm_count, st);
     if (e != cudaSuccess) return fail_cuda(e, "msda_module_backward launch");
     if (staged) {
-        e = msda::launch_round_grad_img(grad_value, static_cast<const float *>(accum), (long long)img_elems, prob->dtype, st);
+        e = msda::launch_round_grad_img(grad_value, static_cast<const float *>(accum), (long long)img_elems, prob->dtype,
+                                        (int)prob->D, (int)(prob->D / 8), st);
         if (e != cudaSuccess) return fail_cuda(e, "msda_module_backward grad_value rounding");
     }
     return MSDA_OK;

@@ -225,22 +225,35 @@ cudaError_t launch_backward_generic(const KernelArgs &a, int dtype, int vec, int
 
 // ---------------------------------------------------------------------------------------------------------------
 // 16-bit storage epilogue: grad_img[T] = round(accumulation image[fp32]).
+// `permuted_lanes` != 0: the image was produced by the tuned kernels, whose rows store channel 8j + 4h + e at position
+// 4*lanes*h + 4j + e (see red_add_row in msda_bwd_tiled.cu); 0: natural channel order (generic kernels).
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T> __global__ void round_grad_img_kernel(T *__restrict__ dst, const float *__restrict__ src, long long n) {
+template <typename T>
+__global__ void round_grad_img_kernel(T *__restrict__ dst, const float *__restrict__ src, long long n, int D,
+                                      int permuted_lanes) {
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        dst[i] = Traits<T>::from_ct(src[i]);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        long long s = i;
+        if (permuted_lanes) {
+            const long long row = i / D;
+            const int c = (int)(i - row * D);
+            s = row * D + 4 * permuted_lanes * ((c >> 2) & 1) + 4 * (c >> 3) + (c & 3);
+        }
+        dst[i] = Traits<T>::from_ct(src[s]);
+    }
 }
 
-cudaError_t launch_round_grad_img(void *dst, const float *src, long long n, int dtype, cudaStream_t st) {
+cudaError_t launch_round_grad_img(void *dst, const float *src, long long n, int dtype, int D, int permuted_lanes,
+                                  cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
     const int threads = 256;
     long long want = (n + threads - 1) / threads;
     const int grid = (int)(want > 148 * 32 ? 148 * 32 : want);
     if (dtype == 1)
-        round_grad_img_kernel<__half><<<grid, threads, 0, st>>>(static_cast<__half *>(dst), src, n);
+        round_grad_img_kernel<__half><<<grid, threads, 0, st>>>(static_cast<__half *>(dst), src, n, D, permuted_lanes);
     else if (dtype == 2)
-        round_grad_img_kernel<__nv_bfloat16><<<grid, threads, 0, st>>>(static_cast<__nv_bfloat16 *>(dst), src, n);
+        round_grad_img_kernel<__nv_bfloat16><<<grid, threads, 0, st>>>(static_cast<__nv_bfloat16 *>(dst), src, n, D,
+                                                                      permuted_lanes);
     else
         return cudaErrorInvalidValue;
     return cudaGetLastError();

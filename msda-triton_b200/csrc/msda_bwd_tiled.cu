@@ -18,6 +18,19 @@ namespace msda {
 constexpr int kNeedImg = 1, kNeedPts = 2, kNeedAw = 4;
 constexpr size_t kBwdL2Budget = 48u << 20;  // img + grad_img bytes of one wave of (b,h) slices
 
+// One lane's VEC channels of a grad_img row as 16-byte reductions.  VEC == 4 (fp32 storage): channels 4j..4j+3 are
+// one red.v4 and the LANES lanes of a group cover the row contiguously.  VEC == 8 (16-bit storage, fp32 accumulation
+// image): a lane owns channels 8j..8j+7, i.e. 32 bytes; issued naively the group's two instructions would each touch
+// HALF of every 32-byte sector (measured: 2x the L2 atomic sector operations, backward 1.0 ms instead of 0.5 ms).  The
+// accumulation image is private scratch, so its channel order is permuted instead: channel 8j + 4h + e is stored at
+// position 4*LANES*h + 4j + e, which makes instruction h of all lanes one contiguous 16*LANES-byte run.
+// `dst` already points at position 4j of the row.  launch_round_grad_img() undoes the permutation.
+template <int VEC, int LANES> __device__ __forceinline__ void red_add_row(float *dst, const float (&gv)[VEC]) {
+    red_add_v4(dst, gv[0], gv[1], gv[2], gv[3]);
+    if constexpr (VEC == 8) red_add_v4(dst + 4 * LANES, gv[4], gv[5], gv[6], gv[7]);
+    static_assert(VEC == 4 || VEC == 8, "tuned kernels use 128-bit lanes");
+}
+
 template <int N, int STEP> __device__ __forceinline__ void transpose_reduce(float (&part)[N], const int j) {
     // lanes with bit STEP clear keep the lower half, their partners (j ^ STEP) the upper half
     constexpr int HALF = N / 2;
@@ -37,11 +50,14 @@ template <int N, int STEP> __device__ __forceinline__ void transpose_reduce(floa
 // FUSED = backward of the module core: operands are the raw projection + reference points (see msda_tiled.cuh);
 // the epilogue turns (grad weight, grad point) into grad of the projection triples (softmax backward, 1/shape or
 // ref_wh/2K scaling) and accumulates grad of the reference points with a handful of scalar atomics per unit.
-template <typename T, int LANES, int LK, bool BORDER, int NB, int THREADS, bool FUSED>
+// VEC = channels per lane: 16 bytes per lane by default; the non-fused 16-bit-storage backward runs 8 lanes x 4
+// channels (8-byte gathers) so that its fp32 row adds have the same full-sector shape as the fp32 kernel's.
+template <typename T, int LANES, int LK, bool BORDER, int NB, int THREADS, bool FUSED, int VEC>
 __global__ void __launch_bounds__(THREADS, 1)
     msda_bwd_tiled_kernel(const KernelArgs a, const WaveSchedule ws) {
     using Cfg = TiledCfg<T, LANES, LK>;
-    constexpr int VEC = Cfg::VEC, G = Cfg::G, PPL = Cfg::PPL;
+    constexpr int G = Cfg::G, PPL = Cfg::PPL;
+    using Raw = typename RawSlice<VEC * (int)sizeof(T)>::type;
     static_assert(LANES % NB == 0, "batch must divide the group");
 
     __shared__ Level s_lv[LK];
@@ -59,7 +75,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     const bool need_img = (a.flags & kNeedImg) != 0, need_pts = (a.flags & kNeedPts) != 0,
                need_aw = (a.flags & kNeedAw) != 0;
     const unsigned row_bytes = (unsigned)(a.H * a.D) * (unsigned)sizeof(T);
-    constexpr unsigned kAccScale = sizeof(float) * VEC / 16;  // accumulation row bytes / storage row bytes
+    constexpr unsigned kAccScale = sizeof(float) / sizeof(T);  // accumulation row bytes / storage row bytes
 
     const int tiles_per_bh = ws.tiles_per_bh;
     for (int wave = 0; wave < ws.waves; ++wave) {
@@ -87,7 +103,9 @@ __global__ void __launch_bounds__(THREADS, 1)
 
         const unsigned char *__restrict__ lane_base =
             reinterpret_cast<const unsigned char *>(img + tu.bh_off + j * VEC);
-        unsigned char *__restrict__ gimg_base = reinterpret_cast<unsigned char *>(gimg + tu.bh_off + j * VEC);
+        // fp32 accumulation row of this (b,h): for 16-bit storage (VEC == 8) the row is kept in the PERMUTED channel
+        // order of accum_position() so that each red.v4 instruction of a lane group covers whole 32-byte sectors
+        unsigned char *__restrict__ gimg_base = reinterpret_cast<unsigned char *>(gimg + tu.bh_off + j * 4);
         // padding queries of the last tile shadow a real query: their image contributions are scaled to zero
         const float live_scale = tu.live ? 1.0f : 0.0f;
 
@@ -108,7 +126,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         for (int pp = 0; pp < PPL; ++pp) {
 #pragma unroll
             for (int jj0 = 0; jj0 < LANES; jj0 += NB) {
-                uint4 raw[NB][4];
+                Raw raw[NB][4];
                 float fx[NB], fy[NB], fw[NB];
                 unsigned o[NB][4];
                 unsigned msk[NB];
@@ -124,7 +142,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                     msk[n] = BORDER ? 0xFu : ((pack >> kPackMaskShift) & 0xFu);
                     // always in range (clamped rows); zeros padding is applied to the dot products below
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) raw[n][c] = gather_row(lane_base, o[n][c]);
+                    for (int c = 0; c < 4; ++c) raw[n][c] = gather_slice<VEC * (int)sizeof(T)>(lane_base, o[n][c]);
                 }
 #pragma unroll
                 for (int n = 0; n < NB; ++n) {
@@ -149,7 +167,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll
                             for (int e = 0; e < VEC; ++e) gv[e] = go[e] * s;
                             float *dst = reinterpret_cast<float *>(gimg_base + (size_t)o[n][c] * kAccScale);
-                            if (BORDER || ((msk[n] >> c) & 1u)) red_add_vec<VEC>(dst, gv);
+                            if (BORDER || ((msk[n] >> c) & 1u)) red_add_row<VEC, LANES>(dst, gv);
                         }
                     }
                     const int pidx = (jj0 + n) * PPL + pp;
@@ -256,7 +274,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 }
 
 
-template <typename T, int LANES, int LK, bool FUSED = false>
+template <typename T, int LANES, int LK, bool FUSED = false, int VEC = 16 / (int)sizeof(T)>
 static cudaError_t launch_tiled_t(const KernelArgs &a, int sm_count, cudaStream_t st) {
     constexpr int THREADS = 512, NB = 2;
     constexpr int G = TiledCfg<T, LANES, LK>::G;
@@ -270,9 +288,9 @@ static cudaError_t launch_tiled_t(const KernelArgs &a, int sm_count, cudaStream_
     const size_t per_slice_factor = (a.flags & kNeedImg) ? sizeof(T) + sizeof(float) : sizeof(T);
     const WaveSchedule ws = make_wave_schedule(a, tiles_per_bh, per_slice_factor, kBwdL2Budget);
     if (a.border)
-        msda_bwd_tiled_kernel<T, LANES, LK, true, NB, THREADS, FUSED><<<grid, THREADS, 0, st>>>(a, ws);
+        msda_bwd_tiled_kernel<T, LANES, LK, true, NB, THREADS, FUSED, VEC><<<grid, THREADS, 0, st>>>(a, ws);
     else
-        msda_bwd_tiled_kernel<T, LANES, LK, false, NB, THREADS, FUSED><<<grid, THREADS, 0, st>>>(a, ws);
+        msda_bwd_tiled_kernel<T, LANES, LK, false, NB, THREADS, FUSED, VEC><<<grid, THREADS, 0, st>>>(a, ws);
     return cudaGetLastError();
 }
 
@@ -312,11 +330,11 @@ cudaError_t launch_backward_tiled(const KernelArgs &a, int dtype, int sm_count, 
         if (a.D == 32) return launch_tiled_t<float, 8, 16>(a, sm_count, st);
         if (a.D == 64) return launch_tiled_t<float, 16, 16>(a, sm_count, st);
     } else if (dtype == 1) {
-        if (a.D == 32) return launch_tiled_t<__half, 4, 16>(a, sm_count, st);
-        if (a.D == 64) return launch_tiled_t<__half, 8, 16>(a, sm_count, st);
+        if (a.D == 32) return launch_tiled_t<__half, 8, 16, false, 4>(a, sm_count, st);
+        if (a.D == 64) return launch_tiled_t<__half, 16, 16, false, 4>(a, sm_count, st);
     } else if (dtype == 2) {
-        if (a.D == 32) return launch_tiled_t<__nv_bfloat16, 4, 16>(a, sm_count, st);
-        if (a.D == 64) return launch_tiled_t<__nv_bfloat16, 8, 16>(a, sm_count, st);
+        if (a.D == 32) return launch_tiled_t<__nv_bfloat16, 8, 16, false, 4>(a, sm_count, st);
+        if (a.D == 64) return launch_tiled_t<__nv_bfloat16, 16, 16, false, 4>(a, sm_count, st);
     }
     return cudaErrorNotSupported;
 }

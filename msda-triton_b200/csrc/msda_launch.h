@@ -29,6 +29,8 @@ size_t det_workspace_bytes(const KernelArgs &a);
 cudaError_t launch_backward_det(const KernelArgs &a, int dtype, int vec, void *workspace, int sm_count, cudaStream_t st);
 
 // grad_img epilogue for 16-bit storage: rounds the fp32 accumulation image to T.
-cudaError_t launch_round_grad_img(void *dst, const float *src, long long n, int dtype, cudaStream_t st);
+// permuted_lanes = D/8 when the image was written by the tuned kernels (channel-permuted rows), 0 for natural order.
+cudaError_t launch_round_grad_img(void *dst, const float *src, long long n, int dtype, int D, int permuted_lanes,
+                                  cudaStream_t st);
 
 }  // namespace msda

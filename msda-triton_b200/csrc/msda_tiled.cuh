@@ -217,12 +217,34 @@ __device__ __forceinline__ void derive_operands(const KernelArgs &a, const Level
     }
 }
 
-// 128-bit read-only gather of one corner row slice (VEC storage elements, kept raw until they are consumed).
-__device__ __forceinline__ uint4 gather_row(const unsigned char *__restrict__ lane_base, unsigned byte_off) {
-    return __ldg(reinterpret_cast<const uint4 *>(lane_base + byte_off));
+// Read-only gather of one lane's slice of a corner row (16 bytes, or 8 bytes for the 16-bit-storage backward that runs
+// 8 lanes x 4 channels), kept raw until it is consumed.
+template <int BYTES> struct RawSlice;
+template <> struct RawSlice<16> { using type = uint4; };
+template <> struct RawSlice<8> { using type = uint2; };
+
+template <int BYTES>
+__device__ __forceinline__ typename RawSlice<BYTES>::type gather_slice(const unsigned char *__restrict__ lane_base,
+                                                                       unsigned byte_off) {
+    return __ldg(reinterpret_cast<const typename RawSlice<BYTES>::type *>(lane_base + byte_off));
 }
 
-// Widens the raw 128 bits to fp32 (VEC = 4 for fp32 storage, 8 for fp16 / bf16 storage).
+__device__ __forceinline__ uint4 gather_row(const unsigned char *__restrict__ lane_base, unsigned byte_off) {
+    return gather_slice<16>(lane_base, byte_off);
+}
+
+template <typename T> __device__ __forceinline__ void widen_word(unsigned r, float &lo, float &hi) {
+    if constexpr (std::is_same<T, __half>::value) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&r));
+        lo = f.x;
+        hi = f.y;
+    } else {
+        lo = __uint_as_float(r << 16);            // bf16 -> fp32 is a 16-bit shift
+        hi = __uint_as_float(r & 0xffff0000u);
+    }
+}
+
+// Widens a raw slice to fp32: VEC = 4 (fp32 x 16 B, or 16-bit x 8 B) or 8 (16-bit x 16 B).
 template <typename T, int VEC> __device__ __forceinline__ void widen_row(const uint4 raw, float (&v)[VEC]) {
     if constexpr (sizeof(T) == 4) {
         v[0] = __uint_as_float(raw.x);
@@ -230,20 +252,16 @@ template <typename T, int VEC> __device__ __forceinline__ void widen_row(const u
         v[2] = __uint_as_float(raw.z);
         v[3] = __uint_as_float(raw.w);
     } else {
-        const unsigned r[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if constexpr (std::is_same<T, __half>::value) {
-                const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&r[i]));
-                v[2 * i] = f.x;
-                v[2 * i + 1] = f.y;
-            } else {
-                // bf16 -> fp32 is a 16-bit shift
-                v[2 * i] = __uint_as_float(r[i] << 16);
-                v[2 * i + 1] = __uint_as_float(r[i] & 0xffff0000u);
-            }
-        }
+        widen_word<T>(raw.x, v[0], v[1]);
+        widen_word<T>(raw.y, v[2], v[3]);
+        widen_word<T>(raw.z, v[4], v[5]);
+        widen_word<T>(raw.w, v[6], v[7]);
     }
+}
+template <typename T, int VEC> __device__ __forceinline__ void widen_row(const uint2 raw, float (&v)[VEC]) {
+    static_assert(sizeof(T) == 2 && VEC == 4, "8-byte slices hold four 16-bit channels");
+    widen_word<T>(raw.x, v[0], v[1]);
+    widen_word<T>(raw.y, v[2], v[3]);
 }
 
 }  // namespace msda

@@ -32,6 +32,9 @@ def timeit(fn, reps=20, warm=3):
 for name in [a for a in sys.argv[1:] if not a.startswith('--')] or list(bench.WORKLOADS):
     B, Q, H, D, pyr, Kp, pm, ac = bench.WORKLOADS[name]
     t, s = bench.make_inputs(name, 0, device="cuda")
+    for dt in ("bf16", "f16"):
+        if "--" + dt in sys.argv:
+            t = {k: v.to(torch.bfloat16 if dt == "bf16" else torch.float16) for k, v in t.items()}
     fwd = timeit(lambda: K.b200_multi_scale_deformable_attention_fwd(t["img"], s, t["pts"], t["aw"], pm, ac))
     res = {"fwd": fwd}
     for label, needs in (("bwd_all", (1, 1, 1)), ("bwd_img_only", (1, 0, 0)), ("bwd_no_img", (0, 1, 1))):
