@@ -312,7 +312,13 @@ static bool split_backward_enabled() {
 }
 
 cudaError_t launch_backward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st) {
-    if (a.LK != 16 || a.L > 16) return cudaErrorNotSupported;
+    if (a.L > 8) return cudaErrorNotSupported;
+    if (a.LK == 8 && a.D == 32) {
+        if (dtype == 0) return launch_tiled_t<float, 8, 8>(a, sm_count, st);
+        if (dtype == 1) return launch_tiled_t<__half, 8, 8, false, 4>(a, sm_count, st);
+        if (dtype == 2) return launch_tiled_t<__nv_bfloat16, 8, 8, false, 4>(a, sm_count, st);
+    }
+    if (a.LK != 16) return cudaErrorNotSupported;
     if ((a.flags & kNeedImg) && dtype == 0 && a.D == 32 && split_backward_enabled()) {
         KernelArgs k1 = a;
         k1.flags &= ~kNeedImg;

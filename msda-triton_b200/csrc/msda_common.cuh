@@ -127,26 +127,53 @@ template <> struct RawWord<16> { using type = uint4; };
 
 template <typename T, int N>
 __device__ __forceinline__ void load_vec_stream(const T *__restrict__ p, typename Traits<T>::CT (&dst)[N]) {
-    using W = typename RawWord<sizeof(T) * N>::type;
-    union {
-        W w;
-        Pack<T, N> pack;
-    } u;
-    u.w = __ldcs(reinterpret_cast<const W *>(p));
+    constexpr int kBytes = (int)sizeof(T) * N;
+    if constexpr (kBytes > 16) {
+        // wider than one 128-bit access: consecutive 16-byte pieces
+        constexpr int E16 = 16 / (int)sizeof(T);
+        static_assert(N % E16 == 0, "wide streaming loads must be a whole number of 16-byte pieces");
 #pragma unroll
-    for (int i = 0; i < N; ++i) dst[i] = Traits<T>::to_ct(u.pack.v[i]);
+        for (int c = 0; c < N / E16; ++c) {
+            typename Traits<T>::CT piece[E16];
+            load_vec_stream<T, E16>(p + c * E16, piece);
+#pragma unroll
+            for (int e = 0; e < E16; ++e) dst[c * E16 + e] = piece[e];
+        }
+    } else {
+        using W = typename RawWord<kBytes>::type;
+        union {
+            W w;
+            Pack<T, N> pack;
+        } u;
+        u.w = __ldcs(reinterpret_cast<const W *>(p));
+#pragma unroll
+        for (int i = 0; i < N; ++i) dst[i] = Traits<T>::to_ct(u.pack.v[i]);
+    }
 }
 
 template <typename T, int N>
 __device__ __forceinline__ void store_vec_stream(T *__restrict__ p, const typename Traits<T>::CT (&src)[N]) {
-    using W = typename RawWord<sizeof(T) * N>::type;
-    union {
-        W w;
-        Pack<T, N> pack;
-    } u;
+    constexpr int kBytes = (int)sizeof(T) * N;
+    if constexpr (kBytes > 16) {
+        constexpr int E16 = 16 / (int)sizeof(T);
+        static_assert(N % E16 == 0, "wide streaming stores must be a whole number of 16-byte pieces");
 #pragma unroll
-    for (int i = 0; i < N; ++i) u.pack.v[i] = Traits<T>::from_ct(src[i]);
-    __stcs(reinterpret_cast<W *>(p), u.w);
+        for (int c = 0; c < N / E16; ++c) {
+            typename Traits<T>::CT piece[E16];
+#pragma unroll
+            for (int e = 0; e < E16; ++e) piece[e] = src[c * E16 + e];
+            store_vec_stream<T, E16>(p + c * E16, piece);
+        }
+    } else {
+        using W = typename RawWord<kBytes>::type;
+        union {
+            W w;
+            Pack<T, N> pack;
+        } u;
+#pragma unroll
+        for (int i = 0; i < N; ++i) u.pack.v[i] = Traits<T>::from_ct(src[i]);
+        __stcs(reinterpret_cast<W *>(p), u.w);
+    }
 }
 
 // Round-to-nearest mul / sub that the compiler may NOT contract into an FMA: the reference writes

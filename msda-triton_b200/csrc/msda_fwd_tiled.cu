@@ -148,18 +148,27 @@ static cudaError_t launch_tiled_t(const KernelArgs &a, int sm_count, cudaStream_
     return launch_tiled_cfg<T, LANES, LK, 1024, 2>(a, sm_count, st);
 }
 
-// Eligibility: L*K == 16, one pixel-row slice is LANES x 16 bytes with LANES in the instantiated set.
+// Eligibility: L*K in {8, 16, 32} sampling points, one pixel-row slice is LANES x 16 bytes with LANES in the
+// instantiated set (anything else runs the generic kernel).
 cudaError_t launch_forward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st) {
-    if (a.LK != 16 || a.L > 16) return cudaErrorNotSupported;
-    if (dtype == 0) {
-        if (a.D == 32) return launch_tiled_t<float, 8, 16>(a, sm_count, st);
-        if (a.D == 64) return launch_tiled_t<float, 16, 16>(a, sm_count, st);
-    } else if (dtype == 1) {
-        if (a.D == 32) return launch_tiled_t<__half, 4, 16>(a, sm_count, st);
-        if (a.D == 64) return launch_tiled_t<__half, 8, 16>(a, sm_count, st);
-    } else if (dtype == 2) {
-        if (a.D == 32) return launch_tiled_t<__nv_bfloat16, 4, 16>(a, sm_count, st);
-        if (a.D == 64) return launch_tiled_t<__nv_bfloat16, 8, 16>(a, sm_count, st);
+    if (a.L > 8) return cudaErrorNotSupported;
+    if (a.LK == 16) {
+        if (dtype == 0) {
+            if (a.D == 32) return launch_tiled_t<float, 8, 16>(a, sm_count, st);
+            if (a.D == 64) return launch_tiled_t<float, 16, 16>(a, sm_count, st);
+        } else if (dtype == 1) {
+            if (a.D == 32) return launch_tiled_t<__half, 4, 16>(a, sm_count, st);
+            if (a.D == 64) return launch_tiled_t<__half, 8, 16>(a, sm_count, st);
+        } else if (dtype == 2) {
+            if (a.D == 32) return launch_tiled_t<__nv_bfloat16, 4, 16>(a, sm_count, st);
+            if (a.D == 64) return launch_tiled_t<__nv_bfloat16, 8, 16>(a, sm_count, st);
+        }
+    } else if (a.LK == 8 && a.D == 32) {
+        if (dtype == 0) return launch_tiled_t<float, 8, 8>(a, sm_count, st);
+        if (dtype == 1) return launch_tiled_t<__half, 4, 8>(a, sm_count, st);
+        if (dtype == 2) return launch_tiled_t<__nv_bfloat16, 4, 8>(a, sm_count, st);
+    } else if (a.LK == 32 && a.D == 32 && dtype == 0) {
+        return launch_tiled_t<float, 8, 32>(a, sm_count, st);
     }
     return cudaErrorNotSupported;
 }

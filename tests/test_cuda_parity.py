@@ -106,6 +106,9 @@ CASES = {
     "one_level_one_point": (2, 50, 3, 16, [(7, 9)], 1, "far", "softmax_lk"),
     "wide_channels": (1, 40, 2, 200, [(6, 6), (3, 3)], 2, "wide", "softmax_lk"),      # D > 32*4: channel chunks
     "many_points": (1, 30, 2, 8, [(6, 6), (3, 3), (2, 2)], 19, "wide", "softmax_lk"), # L*K = 57 > 32 lanes
+    "lk8_two_levels": (2, 501, 8, 32, [(20, 30), (10, 15)], 4, "wide", "softmax_lk"),  # tuned kernels, L*K = 8
+    "lk8_one_level": (2, 300, 8, 32, [(24, 31)], 8, "far", "softmax_lk"),             # tuned kernels, L = 1
+    "lk32_k8": (2, 403, 8, 32, BENCH_PYRAMID, 8, "wide", "softmax_lk"),               # tuned forward, L*K = 32
 }
 
 
@@ -146,7 +149,7 @@ def _bounds(dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
-@pytest.mark.parametrize("D,Kp", [(32, 4), (64, 4), (32, 3), (4, 8)])
+@pytest.mark.parametrize("D,Kp", [(32, 4), (64, 4), (32, 3), (4, 8), (32, 2)])
 @pytest.mark.parametrize("pm,ac", MODES)
 def test_16bit_storage_bounds(K, oracle, dtype, D, Kp, pm, ac):
     """16-bit STORAGE, fp32 compute: against the fp64 oracle evaluated on the same (already rounded) inputs every
