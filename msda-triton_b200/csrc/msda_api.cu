@@ -312,7 +312,7 @@ int msda_backward(void *grad_img, void *grad_points, void *grad_weights, const v
 int msda_module_supported(const msda_problem *prob, int ref_dim) {
     if (validate(prob) != MSDA_OK) return 0;
     if (ref_dim != 2 && ref_dim != 4) return 0;
-    if (prob->dtype == MSDA_DTYPE_F64 || prob->D != 32 || prob->L * prob->K != 16 || prob->L > 16) return 0;
+    if (prob->dtype == MSDA_DTYPE_F64 || prob->D != 32 || prob->L * prob->K != 16 || prob->L > 8) return 0;
     msda::KernelArgs a;
     fill_args(a, prob, 1);
     return msda::tiled_offsets_fit(a, dtype_size(prob->dtype)) ? 1 : 0;

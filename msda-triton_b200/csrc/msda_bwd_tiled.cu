@@ -52,7 +52,8 @@ template <int N, int STEP> __device__ __forceinline__ void transpose_reduce(floa
 // ref_wh/2K scaling) and accumulates grad of the reference points with a handful of scalar atomics per unit.
 // VEC = channels per lane: 16 bytes per lane by default; the non-fused 16-bit-storage backward runs 8 lanes x 4
 // channels (8-byte gathers) so that its fp32 row adds have the same full-sector shape as the fp32 kernel's.
-template <typename T, int LANES, int LK, bool BORDER, int NB, int THREADS, bool FUSED, int VEC>
+// PADDED: see the forward kernel -- a.LK <= LK real points, dead slots skipped warp-uniformly, per-point stores.
+template <typename T, int LANES, int LK, bool BORDER, int NB, int THREADS, bool FUSED, int VEC, bool PADDED>
 __global__ void __launch_bounds__(THREADS, 1)
     msda_bwd_tiled_kernel(const KernelArgs a, const WaveSchedule ws) {
     using Cfg = TiledCfg<T, LANES, LK>;
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     using Raw = typename RawSlice<VEC * (int)sizeof(T)>::type;
     static_assert(LANES % NB == 0, "batch must divide the group");
 
-    __shared__ Level s_lv[LK];
+    __shared__ Level s_lv[8];   // tuned kernels take L <= 8
     build_level_table(s_lv, a.shapes, a.L);
 
     const T *__restrict__ img = static_cast<const T *>(a.img);
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     TileUnit tu = decode_tile(tile, tiles_per_bh, g, G, a);
     LaneOperands<T, PPL, FUSED> op;
     float go[VEC];
-    load_operands<T, LANES, LK, FUSED>(a, tu, j, op);
+    load_operands<T, LANES, LK, FUSED, PADDED>(a, tu, j, op);
     load_vec_stream<T, VEC>(gout + (size_t)tu.u * a.D + j * VEC, go);
 
     for (; tile < t_end; tile += nwarps) {
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         const TileUnit tu_n = decode_tile(has_next ? tile_n : tile, tiles_per_bh, g, G, a);
         LaneOperands<T, PPL, FUSED> op_n;
         float go_n[VEC];
-        load_operands<T, LANES, LK, FUSED>(a, tu_n, j, op_n);
+        load_operands<T, LANES, LK, FUSED, PADDED>(a, tu_n, j, op_n);
         load_vec_stream<T, VEC>(gout + (size_t)tu_n.u * a.D + j * VEC, go_n);
         if constexpr (FUSED) derive_operands<T, LANES, LK>(a, s_lv, j, op);
 
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         float sx[PPL], sy[PPL];
 #pragma unroll
         for (int pp = 0; pp < PPL; ++pp) {
-            const Level lv = s_lv[(j * PPL + pp) / a.K];
+            const Level lv = s_lv[slot_level(j * PPL + pp, a)];
             tap[pp] = resolve_tap<BORDER>(op.xy[2 * pp], op.xy[2 * pp + 1], lv, align, row_bytes);
             sx[pp] = align ? (float)(lv.w - 1) : (float)lv.w;
             sy[pp] = align ? (float)(lv.h - 1) : (float)lv.h;
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll
                 for (int n = 0; n < NB; ++n) {
                     const int src = jj0 + n;
+                    if (PADDED && src * PPL + pp >= a.LK) continue;   // dead slot (warp-uniform)
                     const unsigned off = __shfl_sync(0xffffffffu, tap[pp].off, src, LANES);
                     const unsigned pack = __shfl_sync(0xffffffffu, tap[pp].pack, src, LANES);
                     fx[n] = __shfl_sync(0xffffffffu, tap[pp].dx, src, LANES);
@@ -146,6 +148,11 @@ __global__ void __launch_bounds__(THREADS, 1)
                 }
 #pragma unroll
                 for (int n = 0; n < NB; ++n) {
+                    if (PADDED && (jj0 + n) * PPL + pp >= a.LK) {
+                        const int dead = (jj0 + n) * PPL + pp;
+                        part[3 * dead + 0] = part[3 * dead + 1] = part[3 * dead + 2] = 0.0f;
+                        continue;
+                    }
                     const float dx = fx[n], dy = fy[n];
                     float bw[4];  // bilinear weights of corners 00, 01, 10, 11
                     bw[1] = (1.0f - dy) * dx;
@@ -183,20 +190,40 @@ __global__ void __launch_bounds__(THREADS, 1)
 
         if constexpr (!FUSED) {
             if (tu.live) {
-                if (need_aw) {
-                    float gw[PPL];
+                T *__restrict__ gaw_u = gaw + (size_t)tu.u * a.LK;
+                T *__restrict__ gpts_u = gpts + (size_t)tu.u * a.LK * 2;
+                if constexpr (!PADDED) {
+                    if (need_aw) {
+                        float gw[PPL];
 #pragma unroll
-                    for (int pp = 0; pp < PPL; ++pp) gw[pp] = part[3 * pp + 0];
-                    store_vec_stream<T, PPL>(gaw + (size_t)tu.u * LK + j * PPL, gw);
-                }
-                if (need_pts) {
-                    float gp[2 * PPL];
+                        for (int pp = 0; pp < PPL; ++pp) gw[pp] = part[3 * pp + 0];
+                        store_vec_stream<T, PPL>(gaw_u + j * PPL, gw);
+                    }
+                    if (need_pts) {
+                        float gp[2 * PPL];
+#pragma unroll
+                        for (int pp = 0; pp < PPL; ++pp) {
+                            gp[2 * pp + 0] = part[3 * pp + 1] * (op.wa[pp] * sx[pp]);
+                            gp[2 * pp + 1] = part[3 * pp + 2] * (op.wa[pp] * sy[pp]);
+                        }
+                        store_vec_stream<T, 2 * PPL>(gpts_u + j * PPL * 2, gp);
+                    }
+                } else {
 #pragma unroll
                     for (int pp = 0; pp < PPL; ++pp) {
-                        gp[2 * pp + 0] = part[3 * pp + 1] * (op.wa[pp] * sx[pp]);
-                        gp[2 * pp + 1] = part[3 * pp + 2] * (op.wa[pp] * sy[pp]);
+                        const int p = j * PPL + pp;
+                        if (p < a.LK) {
+                            if (need_aw) {
+                                const float gw1[1] = {part[3 * pp + 0]};
+                                store_vec_stream<T, 1>(gaw_u + p, gw1);
+                            }
+                            if (need_pts) {
+                                const float gp2[2] = {part[3 * pp + 1] * (op.wa[pp] * sx[pp]),
+                                                      part[3 * pp + 2] * (op.wa[pp] * sy[pp])};
+                                store_vec_stream<T, 2>(gpts_u + 2 * p, gp2);
+                            }
+                        }
                     }
-                    store_vec_stream<T, 2 * PPL>(gpts + ((size_t)tu.u * LK + j * PPL) * 2, gp);
                 }
             }
         } else {
@@ -274,7 +301,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 }
 
 
-template <typename T, int LANES, int LK, bool FUSED = false, int VEC = 16 / (int)sizeof(T)>
+template <typename T, int LANES, int LK, bool FUSED = false, int VEC = 16 / (int)sizeof(T), bool PADDED = false>
 static cudaError_t launch_tiled_t(const KernelArgs &a, int sm_count, cudaStream_t st) {
     constexpr int THREADS = 512, NB = 2;
     constexpr int G = TiledCfg<T, LANES, LK>::G;
@@ -288,15 +315,15 @@ static cudaError_t launch_tiled_t(const KernelArgs &a, int sm_count, cudaStream_
     const size_t per_slice_factor = (a.flags & kNeedImg) ? sizeof(T) + sizeof(float) : sizeof(T);
     const WaveSchedule ws = make_wave_schedule(a, tiles_per_bh, per_slice_factor, kBwdL2Budget);
     if (a.border)
-        msda_bwd_tiled_kernel<T, LANES, LK, true, NB, THREADS, FUSED, VEC><<<grid, THREADS, 0, st>>>(a, ws);
+        msda_bwd_tiled_kernel<T, LANES, LK, true, NB, THREADS, FUSED, VEC, PADDED><<<grid, THREADS, 0, st>>>(a, ws);
     else
-        msda_bwd_tiled_kernel<T, LANES, LK, false, NB, THREADS, FUSED, VEC><<<grid, THREADS, 0, st>>>(a, ws);
+        msda_bwd_tiled_kernel<T, LANES, LK, false, NB, THREADS, FUSED, VEC, PADDED><<<grid, THREADS, 0, st>>>(a, ws);
     return cudaGetLastError();
 }
 
 // Backward of the fused module core; same eligibility as launch_module_forward_tiled.
 cudaError_t launch_module_backward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st) {
-    if (a.LK != 16 || a.L > 16 || a.D != 32 || (a.ref_dim != 2 && a.ref_dim != 4)) return cudaErrorNotSupported;
+    if (a.LK != 16 || a.L > 8 || a.D != 32 || (a.ref_dim != 2 && a.ref_dim != 4)) return cudaErrorNotSupported;
     if (dtype == 0) return launch_tiled_t<float, 8, 16, true>(a, sm_count, st);
     if (dtype == 1) return launch_tiled_t<__half, 4, 16, true>(a, sm_count, st);
     if (dtype == 2) return launch_tiled_t<__nv_bfloat16, 4, 16, true>(a, sm_count, st);
@@ -312,13 +339,24 @@ static bool split_backward_enabled() {
 }
 
 cudaError_t launch_backward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st) {
-    if (a.L > 8) return cudaErrorNotSupported;
-    if (a.LK == 8 && a.D == 32) {
-        if (dtype == 0) return launch_tiled_t<float, 8, 8>(a, sm_count, st);
-        if (dtype == 1) return launch_tiled_t<__half, 8, 8, false, 4>(a, sm_count, st);
-        if (dtype == 2) return launch_tiled_t<__nv_bfloat16, 8, 8, false, 4>(a, sm_count, st);
+    if (a.L > 8 || a.LK > 16) return cudaErrorNotSupported;   // 3*L*K partials live in registers: up to 16 points
+    if (a.LK != 16) {
+        if (a.D != 32) return cudaErrorNotSupported;
+        if (a.LK == 8) {
+            if (dtype == 0) return launch_tiled_t<float, 8, 8>(a, sm_count, st);
+            if (dtype == 1) return launch_tiled_t<__half, 8, 8, false, 4>(a, sm_count, st);
+            if (dtype == 2) return launch_tiled_t<__nv_bfloat16, 8, 8, false, 4>(a, sm_count, st);
+        } else if (a.LK < 8) {
+            if (dtype == 0) return launch_tiled_t<float, 8, 8, false, 4, true>(a, sm_count, st);
+            if (dtype == 1) return launch_tiled_t<__half, 8, 8, false, 4, true>(a, sm_count, st);
+            if (dtype == 2) return launch_tiled_t<__nv_bfloat16, 8, 8, false, 4, true>(a, sm_count, st);
+        } else {
+            if (dtype == 0) return launch_tiled_t<float, 8, 16, false, 4, true>(a, sm_count, st);
+            if (dtype == 1) return launch_tiled_t<__half, 8, 16, false, 4, true>(a, sm_count, st);
+            if (dtype == 2) return launch_tiled_t<__nv_bfloat16, 8, 16, false, 4, true>(a, sm_count, st);
+        }
+        return cudaErrorNotSupported;
     }
-    if (a.LK != 16) return cudaErrorNotSupported;
     if ((a.flags & kNeedImg) && dtype == 0 && a.D == 32 && split_backward_enabled()) {
         KernelArgs k1 = a;
         k1.flags &= ~kNeedImg;

@@ -3,6 +3,8 @@
 // Per warp iteration: G = 32/LANES units.  Each lane resolves PPL = LK/LANES points, then the group walks the LK
 // points in batches of NB: 5 shuffles + 4 independent 128-bit gathers per point, 4*NB gathers in flight per lane on
 // top of whatever the compiler hoists from the next batch.
+#include <cstdlib>
+
 #include "msda_common.cuh"
 #include "msda_launch.h"
 #include "msda_tiled.cuh"
@@ -15,14 +17,15 @@ constexpr size_t kFwdL2Budget = 24u << 20;
 // FUSED = the module core (frontend.py:253-289): operands are the raw query projection [.., L, K, 3] and the reference
 // points; softmax and the sampling-point arithmetic happen in registers, sampling_points / attention_weights are never
 // materialised.
-template <typename T, int LANES, int LK, bool BORDER, int NB, int THREADS, bool FUSED>
+// PADDED = the unit has a.LK <= LK points; the LK - a.LK trailing slots are skipped (warp-uniformly) by every loop.
+template <typename T, int LANES, int LK, bool BORDER, int NB, int THREADS, bool FUSED, bool PADDED>
 __global__ void __launch_bounds__(THREADS, 1)
     msda_fwd_tiled_kernel(const KernelArgs a, const WaveSchedule ws) {
     using Cfg = TiledCfg<T, LANES, LK>;
     constexpr int VEC = Cfg::VEC, G = Cfg::G, PPL = Cfg::PPL;
     static_assert(LANES % NB == 0, "batch must divide the group");
 
-    __shared__ Level s_lv[LK];
+    __shared__ Level s_lv[8];   // tuned kernels take L <= 8
     build_level_table(s_lv, a.shapes, a.L);
 
     const T *__restrict__ img = static_cast<const T *>(a.img);
@@ -44,14 +47,14 @@ __global__ void __launch_bounds__(THREADS, 1)
     // software pipeline: sampling points / weights of the next warp tile are in flight while this one is processed
     TileUnit tu = decode_tile(tile, tiles_per_bh, g, G, a);
     LaneOperands<T, PPL, FUSED> op;
-    load_operands<T, LANES, LK, FUSED>(a, tu, j, op);
+    load_operands<T, LANES, LK, FUSED, PADDED>(a, tu, j, op);
 
     for (; tile < t_end; tile += nwarps) {
         const int tile_n = tile + nwarps;
         const bool has_next = tile_n < t_end;
         const TileUnit tu_n = decode_tile(has_next ? tile_n : tile, tiles_per_bh, g, G, a);
         LaneOperands<T, PPL, FUSED> op_n;
-        load_operands<T, LANES, LK, FUSED>(a, tu_n, j, op_n);
+        load_operands<T, LANES, LK, FUSED, PADDED>(a, tu_n, j, op_n);
         if constexpr (FUSED) derive_operands<T, LANES, LK>(a, s_lv, j, op);
 
         const unsigned char *__restrict__ lane_base =
@@ -60,7 +63,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         TileTap tap[PPL];
 #pragma unroll
         for (int pp = 0; pp < PPL; ++pp)
-            tap[pp] = resolve_tap<BORDER>(op.xy[2 * pp], op.xy[2 * pp + 1], s_lv[(j * PPL + pp) / a.K], align, row_bytes);
+            tap[pp] = resolve_tap<BORDER>(op.xy[2 * pp], op.xy[2 * pp + 1], s_lv[slot_level(j * PPL + pp, a)], align, row_bytes);
 
         float acc[VEC];
 #pragma unroll
@@ -76,6 +79,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll
                 for (int n = 0; n < NB; ++n) {
                     const int src = jj0 + n;
+                    if (PADDED && src * PPL + pp >= a.LK) continue;   // dead slot (warp-uniform)
                     const unsigned off = __shfl_sync(0xffffffffu, tap[pp].off, src, LANES);
                     const unsigned pack = __shfl_sync(0xffffffffu, tap[pp].pack, src, LANES);
                     fx[n] = __shfl_sync(0xffffffffu, tap[pp].dx, src, LANES);
@@ -92,6 +96,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                 }
 #pragma unroll
                 for (int n = 0; n < NB; ++n) {
+                    if (PADDED && (jj0 + n) * PPL + pp >= a.LK) continue;
                     const float wy1 = fw[n] * fy[n], wy0 = fw[n] - wy1;  // w*dy, w*(1-dy)
                     float w[4];
                     w[1] = wy0 * fx[n];
@@ -118,7 +123,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     }  // waves
 }
 
-template <typename T, int LANES, int LK, int THREADS, int NB, bool FUSED = false>
+template <typename T, int LANES, int LK, int THREADS, int NB, bool FUSED = false, bool PADDED = false>
 static cudaError_t launch_tiled_cfg(const KernelArgs &a, int sm_count, cudaStream_t st) {
     constexpr int G = TiledCfg<T, LANES, LK>::G;
     if (!tiled_offsets_fit(a, sizeof(T))) return cudaErrorNotSupported;
@@ -129,29 +134,34 @@ static cudaError_t launch_tiled_cfg(const KernelArgs &a, int sm_count, cudaStrea
     const int grid = (int)(want < sm_count ? (want < 1 ? 1 : want) : sm_count);
     const WaveSchedule ws = make_wave_schedule(a, tiles_per_bh, sizeof(T), kFwdL2Budget);
     if (a.border)
-        msda_fwd_tiled_kernel<T, LANES, LK, true, NB, THREADS, FUSED><<<grid, THREADS, 0, st>>>(a, ws);
+        msda_fwd_tiled_kernel<T, LANES, LK, true, NB, THREADS, FUSED, PADDED><<<grid, THREADS, 0, st>>>(a, ws);
     else
-        msda_fwd_tiled_kernel<T, LANES, LK, false, NB, THREADS, FUSED><<<grid, THREADS, 0, st>>>(a, ws);
+        msda_fwd_tiled_kernel<T, LANES, LK, false, NB, THREADS, FUSED, PADDED><<<grid, THREADS, 0, st>>>(a, ws);
     return cudaGetLastError();
 }
 
 // Launch shape.  Measured on B200 (cold L2, fp32 D=32): 1024 threads x 2-point gather batches (64 registers) versus
 // 512 threads x 4-point batches (128 registers): bench shape border 0.147 vs 0.142 ms, zeros 0.153 vs 0.163 ms,
 // DETR encoder 0.173 vs 0.209 ms -- more resident warps hide the L2 latency of the levels that do not fit L1.
-template <typename T, int LANES, int LK>
+template <typename T, int LANES, int LK, bool PADDED = false>
 static cudaError_t launch_tiled_t(const KernelArgs &a, int sm_count, cudaStream_t st) {
-    if (const char *e = std::getenv("MSDA_B200_FWD_VARIANT")) {   // tuning knob
-        if (std::atoi(e) == 1) return launch_tiled_cfg<T, LANES, LK, 512, 4>(a, sm_count, st);
+    if constexpr (!PADDED) {
+        if (const char *e = std::getenv("MSDA_B200_FWD_VARIANT")) {   // tuning knob
+            if (std::atoi(e) == 1) return launch_tiled_cfg<T, LANES, LK, 512, 4>(a, sm_count, st);
+        }
     }
-    // lanes that own 4 points (16-bit storage, D=32) keep more state: stay at 128 registers there
-    if constexpr (TiledCfg<T, LANES, LK>::PPL >= 4) return launch_tiled_cfg<T, LANES, LK, 512, 4>(a, sm_count, st);
-    return launch_tiled_cfg<T, LANES, LK, 1024, 2>(a, sm_count, st);
+    // lanes that own >= 3 points keep more state: stay at 128 registers there
+    if constexpr (TiledCfg<T, LANES, LK>::PPL >= 3)
+        return launch_tiled_cfg<T, LANES, LK, 512, 4, false, PADDED>(a, sm_count, st);
+    else
+        return launch_tiled_cfg<T, LANES, LK, 1024, 2, false, PADDED>(a, sm_count, st);
 }
 
-// Eligibility: L*K in {8, 16, 32} sampling points, one pixel-row slice is LANES x 16 bytes with LANES in the
-// instantiated set (anything else runs the generic kernel).
+// Eligibility: D == 32 (or 64 for L*K == 16) and up to 32 sampling points per unit.  L*K in {8, 16, 32} run exact
+// instantiations; any other L*K <= 32 runs the next larger slot count with the spare slots dead (RT-DETR / Mask2Former
+// style L=3,K=4 -> 12 points, 5-level pyramids -> 20 points, the reference's own K=3 test fixture -> 12 points).
 cudaError_t launch_forward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st) {
-    if (a.L > 8) return cudaErrorNotSupported;
+    if (a.L > 8 || a.LK > 32) return cudaErrorNotSupported;
     if (a.LK == 16) {
         if (dtype == 0) {
             if (a.D == 32) return launch_tiled_t<float, 8, 16>(a, sm_count, st);
@@ -163,19 +173,34 @@ cudaError_t launch_forward_tiled(const KernelArgs &a, int dtype, int sm_count, c
             if (a.D == 32) return launch_tiled_t<__nv_bfloat16, 4, 16>(a, sm_count, st);
             if (a.D == 64) return launch_tiled_t<__nv_bfloat16, 8, 16>(a, sm_count, st);
         }
-    } else if (a.LK == 8 && a.D == 32) {
+        return cudaErrorNotSupported;
+    }
+    if (a.D != 32) return cudaErrorNotSupported;
+    if (a.LK == 8) {
         if (dtype == 0) return launch_tiled_t<float, 8, 8>(a, sm_count, st);
         if (dtype == 1) return launch_tiled_t<__half, 4, 8>(a, sm_count, st);
         if (dtype == 2) return launch_tiled_t<__nv_bfloat16, 4, 8>(a, sm_count, st);
-    } else if (a.LK == 32 && a.D == 32 && dtype == 0) {
-        return launch_tiled_t<float, 8, 32>(a, sm_count, st);
+    } else if (a.LK == 32) {
+        if (dtype == 0) return launch_tiled_t<float, 8, 32>(a, sm_count, st);
+    } else if (a.LK < 8) {
+        if (dtype == 0) return launch_tiled_t<float, 8, 8, true>(a, sm_count, st);
+        if (dtype == 1) return launch_tiled_t<__half, 4, 8, true>(a, sm_count, st);
+        if (dtype == 2) return launch_tiled_t<__nv_bfloat16, 4, 8, true>(a, sm_count, st);
+    } else if (a.LK < 16) {
+        if (dtype == 0) return launch_tiled_t<float, 8, 16, true>(a, sm_count, st);
+        if (dtype == 1) return launch_tiled_t<__half, 4, 16, true>(a, sm_count, st);
+        if (dtype == 2) return launch_tiled_t<__nv_bfloat16, 4, 16, true>(a, sm_count, st);
+    } else if (a.LK < 24) {
+        if (dtype == 0) return launch_tiled_t<float, 8, 24, true>(a, sm_count, st);
+    } else if (a.LK < 32) {
+        if (dtype == 0) return launch_tiled_t<float, 8, 32, true>(a, sm_count, st);
     }
     return cudaErrorNotSupported;
 }
 
 // Fused module core: (fp32 | fp16 | bf16) x D=32 x L*K=16 -- hidden 256 / 8 heads, the Deformable-DETR family.
 cudaError_t launch_module_forward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st) {
-    if (a.LK != 16 || a.L > 16 || a.D != 32 || (a.ref_dim != 2 && a.ref_dim != 4)) return cudaErrorNotSupported;
+    if (a.LK != 16 || a.L > 8 || a.D != 32 || (a.ref_dim != 2 && a.ref_dim != 4)) return cudaErrorNotSupported;
     if (dtype == 0) return launch_tiled_cfg<float, 8, 16, 1024, 2, true>(a, sm_count, st);
     if (dtype == 1) return launch_tiled_cfg<__half, 4, 16, 512, 4, true>(a, sm_count, st);
     if (dtype == 2) return launch_tiled_cfg<__nv_bfloat16, 4, 16, 512, 4, true>(a, sm_count, st);

@@ -100,6 +100,12 @@ __device__ __forceinline__ TileUnit decode_tile(int tile, int tiles_per_bh, int 
     return t;
 }
 
+// Level of point slot p (dead slots of padded instantiations fall back to the last level; their weight is 0).
+__device__ __forceinline__ int slot_level(int p, const KernelArgs &a) {
+    const int l = p / a.K;
+    return l < a.L ? l : a.L - 1;
+}
+
 // One resolved sampling point as exchanged between the lanes of a group (4 registers + the attention weight).
 //   off  : byte offset of the (y0,x0) corner row inside the (b,h) slice           (< 2^28, see tiled_offsets_fit)
 //   pack : bits 0..23 = byte step to the y1 rows / 16, bit 24 = x1 differs from x0, bits 25..28 = corner validity
@@ -146,19 +152,36 @@ template <typename T, int PPL, bool FUSED> struct LaneOperands {
 };
 
 // Issues the (streaming) loads for unit `tu` -- nothing here depends on the loaded values, so the call can sit one
-// warp tile ahead of its use.
-template <typename T, int LANES, int LK, bool FUSED>
+// warp tile ahead of its use.  LK is the number of point SLOTS of the instantiation (LANES * PPL); with PADDED the
+// unit really has a.LK <= LK points, the remaining slots are dead (weight 0, never gathered).
+template <typename T, int LANES, int LK, bool FUSED, bool PADDED = false>
 __device__ __forceinline__ void load_operands(const KernelArgs &a, const TileUnit &tu, int j,
                                               LaneOperands<T, LK / LANES, FUSED> &op) {
     constexpr int PPL = LK / LANES;
     if constexpr (!FUSED) {
-        const T *__restrict__ pts = static_cast<const T *>(a.pts);
-        const T *__restrict__ aw = static_cast<const T *>(a.aw);
-        load_vec_stream<T, 2 * PPL>(pts + ((size_t)tu.u * LK + j * PPL) * 2, op.xy);
-        load_vec_stream<T, PPL>(aw + (size_t)tu.u * LK + j * PPL, op.wa);
+        const T *__restrict__ pts = static_cast<const T *>(a.pts) + (size_t)tu.u * a.LK * 2;
+        const T *__restrict__ aw = static_cast<const T *>(a.aw) + (size_t)tu.u * a.LK;
+        if constexpr (!PADDED) {
+            load_vec_stream<T, 2 * PPL>(pts + j * PPL * 2, op.xy);
+            load_vec_stream<T, PPL>(aw + j * PPL, op.wa);
+        } else {
+#pragma unroll
+            for (int pp = 0; pp < PPL; ++pp) {
+                const int p = j * PPL + pp;
+                float xy2[2] = {0.0f, 0.0f}, w1[1] = {0.0f};
+                if (p < a.LK) {
+                    load_vec_stream<T, 2>(pts + 2 * p, xy2);
+                    load_vec_stream<T, 1>(aw + p, w1);
+                }
+                op.xy[2 * pp] = xy2[0];
+                op.xy[2 * pp + 1] = xy2[1];
+                op.wa[pp] = w1[0];
+            }
+        }
     } else {
         constexpr int E8 = 8 / (int)sizeof(T);            // elements per 8-byte chunk
         static_assert((3 * PPL) % E8 == 0, "fused operands are fetched in 8-byte chunks");
+        static_assert(!PADDED, "the fused module core is instantiated for exact L*K only");
         const T *__restrict__ proj = static_cast<const T *>(a.proj) + ((size_t)tu.u * LK + j * PPL) * 3;
 #pragma unroll
         for (int c = 0; c < 3 * PPL / E8; ++c) {

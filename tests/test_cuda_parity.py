@@ -109,6 +109,10 @@ CASES = {
     "lk8_two_levels": (2, 501, 8, 32, [(20, 30), (10, 15)], 4, "wide", "softmax_lk"),  # tuned kernels, L*K = 8
     "lk8_one_level": (2, 300, 8, 32, [(24, 31)], 8, "far", "softmax_lk"),             # tuned kernels, L = 1
     "lk32_k8": (2, 403, 8, 32, BENCH_PYRAMID, 8, "wide", "softmax_lk"),               # tuned forward, L*K = 32
+    "lk20_five_levels": (2, 350, 8, 32, [(32, 40), (16, 20), (8, 10), (4, 5), (2, 3)], 4, "wide", "softmax_lk"),  # padded 24
+    "lk4_one_level": (2, 350, 8, 32, [(17, 23)], 4, "wide", "softmax_lk"),            # padded 8
+    "lk28_k7": (1, 222, 8, 32, BENCH_PYRAMID, 7, "wide", "softmax_lk"),               # padded 32 (forward)
+    "lk12_rtdetr": (2, 300, 8, 32, [(40, 40), (20, 20), (10, 10)], 4, "unit", "softmax_lk"),  # padded 16 (L=3, K=4)
 }
 
 
@@ -149,7 +153,7 @@ def _bounds(dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
-@pytest.mark.parametrize("D,Kp", [(32, 4), (64, 4), (32, 3), (4, 8), (32, 2)])
+@pytest.mark.parametrize("D,Kp", [(32, 4), (64, 4), (32, 3), (4, 8), (32, 2), (32, 1)])
 @pytest.mark.parametrize("pm,ac", MODES)
 def test_16bit_storage_bounds(K, oracle, dtype, D, Kp, pm, ac):
     """16-bit STORAGE, fp32 compute: against the fp64 oracle evaluated on the same (already rounded) inputs every
