@@ -482,6 +482,15 @@ def run_ours(args):
         if world == 1 and not args.quick:
             try:
                 extra["l2_probe"] = l2_probe(_lib.get_lib())
+                # the resource that actually binds the backward: fp32 row adds into L2 (SURVEY.md 8d "L2 gather /
+                # atomic roof", measured live with the same 8-lane x 128-bit access shape)
+                atomic_peak = extra["l2_probe"]["scatter_gbs"]
+                roofline["onchip"] = {
+                    "bound": "l2_atomic", "unit": "GB/s", "peak": atomic_peak,
+                    "peak_source": "msda_probe_scatter (red.global.add.v4.f32 over an L2-resident buffer), this run",
+                    "achieved": bm["gather"] / (bwd_ms * 1e-3) / 1e9,
+                    "frac": bm["gather"] / (bwd_ms * 1e-3) / 1e9 / atomic_peak,
+                    "note": "bytes = B*Q*H*L*K*4 corner rows of D*4 bytes added into grad_img"}
             except Exception as ex:  # noqa: BLE001
                 extra["l2_probe"] = {"error": str(ex)}
             for name in WORKLOADS:

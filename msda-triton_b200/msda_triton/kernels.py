@@ -15,6 +15,7 @@ Differences from the reference wrappers, all deliberate:
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Literal, Optional, Sequence, Tuple
 
 import torch
@@ -75,6 +76,17 @@ def _shapes_i64(img_shapes: torch.Tensor) -> torch.Tensor:
     return img_shapes.contiguous()
 
 
+def _maybe_validate_shapes(shapes: torch.Tensor, num_pixels: int) -> None:
+    """Like the reference (frontend.py:71-105), the hot path never checks that sum(h*w) equals the pyramid length --
+    doing so needs a device->host sync.  MSDA_B200_VALIDATE=1 turns the check on (debugging aid): the level table is
+    built on the device by the library and read back."""
+    if os.environ.get("MSDA_B200_VALIDATE", "0") == "0":
+        return
+    table = level_table(shapes, num_pixels).cpu()
+    if int(table[-1, 2]) != 1:
+        raise ValueError(f"img_shapes describe {int(table[-1, 0])} pixels but img has {num_pixels}.")
+
+
 def _stream_ptr() -> ctypes.c_void_p:
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -95,6 +107,7 @@ def b200_multi_scale_deformable_attention_fwd(
     img, pts, aw = _dense(img), _dense(sampling_points), _dense(attention_weights)
     shapes = _shapes_i64(img_shapes)
     prob = _problem(img, shapes, pts, aw, padding_mode, align_corners)
+    _maybe_validate_shapes(shapes, prob.Npix)
     out = torch.empty((prob.B, prob.Q, prob.H, prob.D), dtype=img.dtype, device=img.device)
     with torch.cuda.device_of(img):
         rc = _lib.get_lib().msda_forward(_ptr(out), _ptr(img), _ptr(shapes), _ptr(pts), _ptr(aw), ctypes.byref(prob),
@@ -175,6 +188,7 @@ def b200_module_core_fwd(value, img_shapes, proj, ref, padding_mode, align_corne
     value, proj, ref = _dense(value), _dense(proj), _dense(ref)
     shapes = _shapes_i64(img_shapes)
     prob = _module_problem(value, shapes, proj, ref, padding_mode, align_corners)
+    _maybe_validate_shapes(shapes, prob.Npix)
     out = torch.empty((prob.B, prob.Q, prob.H, prob.D), dtype=value.dtype, device=value.device)
     with torch.cuda.device_of(value):
         rc = _lib.get_lib().msda_module_forward(_ptr(out), _ptr(value), _ptr(shapes), _ptr(proj), _ptr(ref),

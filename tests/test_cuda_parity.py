@@ -258,6 +258,19 @@ def test_level_table_on_device(K, oracle):
     assert K.level_table(s, 22222).cpu().numpy()[4, 2] == 0
 
 
+def test_optional_shape_validation(K):
+    img, s, pts, aw, go = make_inputs(1, 8, 2, 32, BENCH_PYRAMID, 4)
+    bad = s.clone()
+    bad[0, 0] += 1
+    os.environ["MSDA_B200_VALIDATE"] = "1"
+    try:
+        K.b200_multi_scale_deformable_attention_fwd(img.cuda(), s.cuda(), pts.cuda(), aw.cuda(), "zeros", False)
+        with pytest.raises(ValueError, match="pixels"):
+            K.b200_multi_scale_deformable_attention_fwd(img.cuda(), bad.cuda(), pts.cuda(), aw.cuda(), "zeros", False)
+    finally:
+        os.environ.pop("MSDA_B200_VALIDATE")
+
+
 def test_int32_shapes_and_cpu_shapes(K, oracle):
     import msda_triton
     img, s, pts, aw, go = make_inputs(1, 64, 2, 32, BENCH_PYRAMID, 4, seed=4)
