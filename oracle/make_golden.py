@@ -117,9 +117,41 @@ def make_inputs(name, dtype):
     return img.to(dtype), shapes_t, pts.to(dtype), aw.to(dtype), go.to(dtype)
 
 
+def make_module_golden(f):
+    """The reference nn.Module (frontend.py:175-292) with seeded weights on CPU: state_dict, inputs, output and the
+    gradients of a scalar loss -- pins the module-level semantics (projection interleaving, softmax over L*K, the
+    (h, w) normaliser of 2-d reference points, the 4-d reference-point formula)."""
+    for coords, pm, ac in ((2, "zeros", False), (4, "border", True)):
+        torch.manual_seed(100 + coords)
+        emb, hidden, levels, heads, points = 16, 64, 4, 2, 4          # head_dim 32, L*K = 16: the fused CUDA shape
+        shapes = [(9, 12), (5, 6), (3, 3), (2, 2)]
+        npix = sum(h * w for h, w in shapes)
+        module = f.MultiscaleDeformableAttention(emb, hidden, levels, heads, points, pm, ac).double()
+        img = torch.randn(2, npix, emb, dtype=torch.float64, requires_grad=True)
+        queries = torch.randn(2, 7, emb, dtype=torch.float64, requires_grad=True)
+        ref = torch.rand(2, 7, coords, dtype=torch.float64)
+        if coords == 4:
+            ref[..., 2:] = ref[..., 2:] * 0.4 + 0.1
+        ref.requires_grad_(True)
+        out = module(img, torch.tensor(shapes), queries, ref)
+        out.square().sum().backward()
+        rec = {f"param.{k}": v.detach().numpy() for k, v in module.state_dict().items()}
+        rec.update({f"grad.{k}": p.grad.numpy() for k, p in module.named_parameters()})
+        rec.update(img=img.detach().numpy(), queries=queries.detach().numpy(), reference_points=ref.detach().numpy(),
+                   img_shapes=np.array(shapes), out=out.detach().numpy(), grad_img=img.grad.numpy(),
+                   grad_queries=queries.grad.numpy(), grad_reference_points=ref.grad.numpy(),
+                   config=np.array([emb, hidden, levels, heads, points, coords, int(ac)]), padding_mode=np.array(pm))
+        path = OUT / f"module_ref{coords}d_float64.npz"
+        np.savez_compressed(path, **rec)
+        print(f"wrote {path}  ({path.stat().st_size / 1024:.1f} KiB)")
+
+
 def main():
     k, f = load_reference()
     OUT.mkdir(parents=True, exist_ok=True)
+    make_module_golden(f)
+    if "--module-only" in sys.argv:
+        return
     for name in CASES:
         for dtype in (torch.float32, torch.float64, torch.float16):
             if dtype == torch.float16 and name not in ("bench_like", "tiny_oob"):

@@ -137,3 +137,13 @@ def test_grid_sample_port_matches_oracle():
     rgi, rgp, rga = msda_oracle.backward(go, img, s, pts, aw, "zeros", False)
     assert_close(to_np(gi), rgi, 1e-9, 1e-10, "grad_img")
     assert_close(to_np(ga), rga, 1e-9, 1e-10, "grad_weights")
+
+
+@pytest.mark.parametrize("name", ["module_ref2d_float64", "module_ref4d_float64"])
+def test_module_matches_reference_module_golden_cpu(name):
+    """Our nn.Module, loaded with the REFERENCE module's state_dict, reproduces the reference module's output and all
+    gradients (golden vectors from oracle/make_golden.py) on the CPU-tensor route."""
+    from conftest import GOLDEN
+    from util import check_module_against_golden, load_module_golden
+    g, module, inputs, shapes = load_module_golden(GOLDEN / f"{name}.npz")
+    check_module_against_golden(g, module, inputs, shapes, rtol=1e-9, atol_scale=1e-11)

@@ -143,3 +143,22 @@ def test_fused_core_rejects_unsupported_and_falls_back():
     out = module(torch.randn(1, 85, 64, device="cuda"), torch.tensor([(8, 8), (4, 4), (2, 2), (1, 1)], device="cuda"),
                  torch.randn(1, 5, 64, device="cuda"), ref)
     assert out.shape == (1, 5, 64)
+
+
+@pytest.mark.parametrize("name", ["module_ref2d_float64", "module_ref4d_float64"])
+@pytest.mark.parametrize("dtype,fused", [(torch.float64, False), (torch.float32, True), (torch.float32, False)],
+                         ids=["f64-composed", "f32-fused", "f32-composed"])
+def test_module_matches_reference_module_golden_cuda(name, dtype, fused):
+    """The reference module's golden output / gradients (seeded weights, CPU, fp64) against our module on CUDA: the
+    composed path in fp64 (generic kernels), and the fused and composed paths in fp32."""
+    from conftest import GOLDEN
+    from util import check_module_against_golden, load_module_golden
+    os.environ["MSDA_B200_FUSED_MODULE"] = "1" if fused else "0"
+    try:
+        g, module, inputs, shapes = load_module_golden(GOLDEN / f"{name}.npz", device="cuda", dtype=dtype)
+        if dtype == torch.float64:
+            check_module_against_golden(g, module, inputs, shapes, rtol=1e-8, atol_scale=1e-10)
+        else:
+            check_module_against_golden(g, module, inputs, shapes, rtol=2e-4, atol_scale=2e-5, max_outliers=2)
+    finally:
+        os.environ.pop("MSDA_B200_FUSED_MODULE")

@@ -53,3 +53,30 @@ def assert_close(test, ref, rtol, atol, what="", max_outliers=0):
             f"{what}: {nbad} / {err.size} elements outside rtol={rtol} atol={atol:.3g}; worst at {idx}: "
             f"test={test[idx]!r} ref={ref[idx]!r} err={err[idx]:.3e}; max|ref|={np.abs(ref).max():.3e}")
     return nbad
+
+
+def load_module_golden(path, device="cpu", dtype=torch.float64):
+    """Rebuilds OUR module from a golden file written by oracle/make_golden.py (reference module, seeded weights)."""
+    from msda_triton import MultiscaleDeformableAttention
+    g = np.load(path)
+    emb, hidden, levels, heads, points, coords, ac = (int(v) for v in g["config"])
+    module = MultiscaleDeformableAttention(emb, hidden, levels, heads, points, str(g["padding_mode"]), bool(ac))
+    state = {k[len("param."):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("param.")}
+    module.load_state_dict(state, strict=True)          # identical parameter names = drop-in checkpoints
+    module = module.to(device=device, dtype=dtype)
+    inputs = {k: torch.from_numpy(g[k]).to(device=device, dtype=dtype).requires_grad_(True)
+              for k in ("img", "queries", "reference_points")}
+    shapes = torch.from_numpy(g["img_shapes"]).to(device)
+    return g, module, inputs, shapes
+
+
+def check_module_against_golden(g, module, inputs, shapes, rtol, atol_scale, max_outliers=0):
+    out = module(inputs["img"], shapes, inputs["queries"], inputs["reference_points"])
+    out.double().square().sum().backward()
+    assert_close(to_np(out), g["out"], rtol, atol_scale * np.abs(g["out"]).max(), "module out", max_outliers)
+    for name, key in (("img", "grad_img"), ("queries", "grad_queries"), ("reference_points", "grad_reference_points")):
+        ref = g[key]
+        assert_close(to_np(inputs[name].grad), ref, rtol, atol_scale * np.abs(ref).max(), key, max_outliers)
+    for name, p in module.named_parameters():
+        ref = g[f"grad.{name}"]
+        assert_close(to_np(p.grad), ref, rtol, atol_scale * np.abs(ref).max(), f"grad {name}", max_outliers)
