@@ -1,21 +1,24 @@
-// msda_bwd_scatter.cu -- grad_img as a separate "scatter-only" kernel (split backward, opt-in / shape-gated).
+// msda_bwd_scatter.cu -- grad_img as a "scatter-only" kernel.
 //
 // grad_img needs only (sampling_points, attention_weights, grad_out) -- the pyramid values are needed just for
-// grad_points / grad_weights.  Splitting the backward into
-//     K1 = the tuned backward without grad_img (gathers, partials; L1 fully available for the pyramid), and
-//     K2 = this kernel (no gathers at all, so the whole 227 KB of shared memory can hold binning state)
-// lifts the conflict measured on the fused binned kernel, where the binning structures pushed the pyramid out of L1.
+// grad_points / grad_weights.  This kernel therefore does no gathers at all, which frees the whole 227 KB of shared
+// memory for an in-CTA segmented reduction of the coarse pyramid levels (in the fused backward such structures push the
+// pyramid out of L1 and cost more than they save: profiles/r1_ncu_summary.md section 4).  It is what msda_backward
+// runs when ONLY grad_img is requested (0.29 ms versus 0.45 ms on the bench shape), and -- together with the tuned
+// backward without grad_img -- the opt-in split backward (MSDA_B200_BWD_SPLIT=1).
 //
-// K2 walks the same persistent (b,h)-major schedule in super-tiles of TQ = 512 queries:
+// The kernel walks the persistent (b,h)-major schedule in super-tiles of TQ queries:
 //   phase A: every lane resolves its PPL points.  Corners in the "binned" levels (the coarsest levels with at most
-//            MAXROWS rows in total, decided on device) are pushed onto a per-row linked list in shared memory
-//            (native 32-bit ATOMS.EXCH on the head; weight + next index stored in natural order, so the query is
-//            implied by the record index).  Corners of the fine levels go straight to L2 as `red.v4.f32`.  The unit's
-//            grad_out row is parked in shared memory.
-//   phase C: one lane group per destination row walks the row's list, accumulates weight * grad_out[q] in registers
-//            and issues ONE `red.v4.f32` per lane for the whole super-tile.
-// For the benchmark pyramid levels 1-3 (1344 rows, 12 of 16 points) are binned: `red` rows per 512 queries drop from
-// 32768 to 8192 + <=1344.
+//            MAXROWS rows in total, decided on device) are pushed onto a linked list in shared memory: one native 32-bit
+//            ATOMS.EXCH on the list head, then an 8-byte record {weight, next | query << 16} in natural order.  Corners
+//            of the fine levels go straight to L2 as `red.v4.f32`.  The unit's grad_out row is parked in shared memory.
+//   phase C: one lane group per list walks it, accumulates weight * grad_out[q] in registers and issues ONE `red.v4.f32`
+//            per lane for the whole super-tile.
+// A destination row of a very coarse level would collect TQ*K*4/rows records (96 for the 8x8 level) while a row of a
+// finer binned level collects a handful; to keep the lane groups of phase C evenly loaded such rows get several lists
+// (split by the low bits of the query index), so that every list is about kTargetList records long.
+// For the benchmark pyramid levels 1-3 (1344 rows, 12 of 16 points) are binned: `red` rows per 384 queries drop from
+// 24576 to 6144 + <= 1536.
 #include <cstdlib>
 
 #include "msda_common.cuh"
@@ -24,7 +27,17 @@
 
 namespace msda {
 
-template <typename T, int LANES, int LK, bool BORDER, int THREADS, int ROUNDS, int MAXROWS, int NBP>
+constexpr int kTargetList = 24;   // records per list phase C aims for
+constexpr int kMaxBinLevels = 8;
+
+struct BinLevel {
+    int level;        // pyramid level
+    int head_base;    // first list head of this level
+    int split_log2;   // lists per destination row = 1 << split_log2
+    int rows;         // h * w
+};
+
+template <typename T, int LANES, int LK, bool BORDER, int THREADS, int ROUNDS, int MAXHEADS, int NBP>
 __global__ void __launch_bounds__(THREADS, 1)
     msda_bwd_scatter_kernel(const KernelArgs a, const int stiles_per_bh, const int total_stiles) {
     using Cfg = TiledCfg<T, LANES, LK>;
@@ -32,33 +45,40 @@ __global__ void __launch_bounds__(THREADS, 1)
     constexpr int NW = THREADS / 32, TQ = NW * G * ROUNDS, NGROUPS = THREADS / LANES;
     constexpr int DCH = LANES * VEC;                       // channels per row (== D)
     constexpr unsigned END = 0xFFFFu;
-    static_assert(TQ * NBP * 4 < 0xFFFF, "record index must fit in 16 bits");
+    static_assert(TQ * NBP * 4 < 0xFFFF && TQ <= 0xFFFF, "record index and query index must fit in 16 bits");
 
     extern __shared__ __align__(16) unsigned char s_dyn[];
-    float *s_w = reinterpret_cast<float *>(s_dyn);                                 // [4][TQ][NBP] record weights
-    float *s_go = s_w + 4 * TQ * NBP;                                              // [TQ][DCH]    grad_out rows
-    unsigned *s_head = reinterpret_cast<unsigned *>(s_go + TQ * DCH);              // [MAXROWS]    list heads
-    unsigned short *s_next = reinterpret_cast<unsigned short *>(s_head + MAXROWS); // [4][TQ][NBP] next record
-    __shared__ Level s_lv[LK];
-    __shared__ int s_bin[3];  // first binned point, first binned pixel row, number of binned rows
+    uint2 *s_rec = reinterpret_cast<uint2 *>(s_dyn);                               // [4][TQ][NBP] {weight, next | q<<16}
+    float *s_go = reinterpret_cast<float *>(s_rec + 4 * TQ * NBP);                 // [TQ][DCH]    grad_out rows
+    unsigned *s_head = reinterpret_cast<unsigned *>(s_go + TQ * DCH);              // [MAXHEADS]   list heads
+    __shared__ Level s_lv[8];
+    __shared__ BinLevel s_bl[kMaxBinLevels];
+    __shared__ int s_bin[3];  // first binned point, number of binned levels, number of list heads
 
     build_level_table(s_lv, a.shapes, a.L);
     if (threadIdx.x == 0) {
-        // binned levels: the longest suffix (coarsest first) with <= MAXROWS rows and <= NBP points per unit
-        int rows = 0, l0 = a.L;
-        for (int l = a.L - 1; l >= 0; --l) {
-            const int n = s_lv[l].h * s_lv[l].w;
-            if (rows + n > MAXROWS || (a.L - l) * a.K > NBP) break;
-            rows += n;
+        // binned levels: the longest suffix (coarsest first) that fits MAXHEADS list heads and NBP points per unit
+        int heads = 0, l0 = a.L, n_bl = 0;
+        for (int l = a.L - 1; l >= 0 && n_bl < kMaxBinLevels; --l) {
+            const int rows = s_lv[l].h * s_lv[l].w;
+            int split_log2 = 0;   // lists per row so that a list holds about kTargetList of the TQ*K*4 records
+            while (split_log2 < 4 && (TQ * a.K * 4) >= (kTargetList << (split_log2 + 1)) * rows) ++split_log2;
+            if (heads + (rows << split_log2) > MAXHEADS || (a.L - l) * a.K > NBP) break;
+            s_bl[n_bl].level = l;
+            s_bl[n_bl].head_base = heads;
+            s_bl[n_bl].split_log2 = split_log2;
+            s_bl[n_bl].rows = rows;
+            heads += rows << split_log2;
+            ++n_bl;
             l0 = l;
         }
         s_bin[0] = l0 * a.K;
-        s_bin[1] = l0 < a.L ? s_lv[l0].off : a.Npix;
-        s_bin[2] = rows;
+        s_bin[1] = n_bl;
+        s_bin[2] = heads;
     }
-    for (int i = threadIdx.x; i < MAXROWS; i += THREADS) s_head[i] = END;
+    for (int i = threadIdx.x; i < MAXHEADS; i += THREADS) s_head[i] = END;
     __syncthreads();
-    const int p0 = s_bin[0], base_row = s_bin[1], nrows = s_bin[2];
+    const int p0 = s_bin[0], n_bl = s_bin[1];
 
     const T *__restrict__ pts = static_cast<const T *>(a.pts);
     const T *__restrict__ aw = static_cast<const T *>(a.aw);
@@ -123,7 +143,8 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll
             for (int pp = 0; pp < PPL; ++pp) {
                 const int p = j * PPL + pp;
-                const Level lv = s_lv[p / a.K];
+                const int l = p / a.K;
+                const Level lv = s_lv[l];
                 const Tap<float> t = locate<float>(xy[2 * pp], xy[2 * pp + 1], lv, BORDER, align);
                 const int step_y = t.pack & kPackDyMask;
                 const int step_x = (t.pack >> kPackDxBit) & 1;
@@ -140,15 +161,17 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) d_w[pp][c] = w4[c];
                 if (p >= p0 && tu.live) {
-                    const int r00 = t.row00 - base_row;
+                    const BinLevel bl = s_bl[a.L - 1 - l];       // binned levels are stored coarsest first
+                    const int r00 = t.row00 - lv.off;
                     const int rows4[4] = {r00, r00 + step_x, r00 + step_y, r00 + step_y + step_x};
+                    const int sub = q_local & ((1 << bl.split_log2) - 1);
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         if (BORDER || ((mask >> c) & 1u)) {
                             const unsigned idx = (unsigned)((c * TQ + q_local) * NBP + (p - p0));
-                            const unsigned prev = atomicExch(&s_head[rows4[c]], idx);
-                            s_next[idx] = (unsigned short)prev;
-                            s_w[idx] = w4[c];
+                            const int head = bl.head_base + (rows4[c] << bl.split_log2) + sub;
+                            const unsigned prev = atomicExch(&s_head[head], idx);
+                            s_rec[idx] = make_uint2(__float_as_uint(w4[c]), prev | ((unsigned)q_local << 16));
                         }
                     }
                 }
@@ -188,32 +211,37 @@ __global__ void __launch_bounds__(THREADS, 1)
             for (int i = 0; i < VEC; ++i) go[i] = go_n[i];
         }
 
-        // ---- phase C: per-row segmented reduction of the binned levels ----
+        // ---- phase C: one lane group per list ----
         __syncthreads();
         {
-            float *__restrict__ gimg_rows = gimg + st_bh_off + (size_t)base_row * row_stride + j * VEC;
             const unsigned group_mask = (LANES == 32 ? 0xffffffffu : ((1u << LANES) - 1u)) << (g * LANES);
-            for (int r = threadIdx.x / LANES; r < nrows; r += NGROUPS) {
-                unsigned idx = END;
-                if (j == 0) {   // the group leader pops the whole list
-                    idx = s_head[r];
-                    s_head[r] = END;
-                }
-                idx = __shfl_sync(group_mask, idx, g * LANES);
-                if (idx != END) {
+            for (int b = 0; b < n_bl; ++b) {
+                const BinLevel bl = s_bl[b];
+                float *__restrict__ gimg_level = gimg + st_bh_off + (size_t)s_lv[bl.level].off * row_stride + j * VEC;
+                const int n_heads = bl.rows << bl.split_log2;
+                for (int hd = threadIdx.x / LANES; hd < n_heads; hd += NGROUPS) {
+                    unsigned idx = END;
+                    if (j == 0) {   // the group leader pops the whole list
+                        idx = s_head[bl.head_base + hd];
+                        s_head[bl.head_base + hd] = END;
+                    }
+                    idx = __shfl_sync(group_mask, idx, g * LANES);
+                    if (idx == END) continue;
                     float acc[VEC];
 #pragma unroll
                     for (int e = 0; e < VEC; ++e) acc[e] = 0.0f;
-                    do {
-                        const float w = s_w[idx];
-                        const unsigned nxt = s_next[idx];
-                        const unsigned q = (idx / NBP) % TQ;
+                    uint2 rec = s_rec[idx];
+                    while (true) {
+                        const unsigned nxt = rec.y & 0xFFFFu;
+                        const unsigned q = rec.y >> 16;
+                        const float w = __uint_as_float(rec.x);
+                        if (nxt != END) rec = s_rec[nxt];            // next record is in flight during the FMAs
                         const Pack<float, VEC> gq = *reinterpret_cast<const Pack<float, VEC> *>(s_go + q * DCH + j * VEC);
 #pragma unroll
                         for (int e = 0; e < VEC; ++e) acc[e] = fmaf(w, gq.v[e], acc[e]);
-                        idx = nxt;
-                    } while (idx != END);
-                    red_add_vec<VEC>(gimg_rows + (size_t)r * row_stride, acc);
+                        if (nxt == END) break;
+                    }
+                    red_add_vec<VEC>(gimg_level + (size_t)(hd >> bl.split_log2) * row_stride, acc);
                 }
             }
         }
@@ -223,13 +251,13 @@ __global__ void __launch_bounds__(THREADS, 1)
 
 template <typename T, int LANES, int LK>
 static cudaError_t launch_scatter_t(const KernelArgs &a, int sm_count, cudaStream_t st) {
-    constexpr int THREADS = 1024, MAXROWS = 1408, NBP = 12;
+    constexpr int THREADS = 1024, MAXHEADS = 2048, NBP = 12;
     using Cfg = TiledCfg<T, LANES, LK>;
-    constexpr int ROUNDS = 512 / ((THREADS / 32) * Cfg::G);   // super-tiles of 512 queries
+    constexpr int ROUNDS = 384 / ((THREADS / 32) * Cfg::G);   // super-tiles of 384 queries
     static_assert(ROUNDS >= 1, "super-tile smaller than one round");
     constexpr int TQ = (THREADS / 32) * Cfg::G * ROUNDS;
-    constexpr size_t kSmem = sizeof(float) * 4 * TQ * NBP + sizeof(float) * TQ * LANES * Cfg::VEC +
-                             sizeof(unsigned) * MAXROWS + sizeof(unsigned short) * 4 * TQ * NBP;
+    constexpr size_t kSmem = sizeof(uint2) * 4 * TQ * NBP + sizeof(float) * TQ * LANES * Cfg::VEC +
+                             sizeof(unsigned) * MAXHEADS;
     static_assert(kSmem <= 227 * 1024, "shared memory budget");
     const int stiles_per_bh = (a.Q + TQ - 1) / TQ;
     const int total_stiles = a.B * a.H * stiles_per_bh;
@@ -240,13 +268,13 @@ static cudaError_t launch_scatter_t(const KernelArgs &a, int sm_count, cudaStrea
         kernel<<<grid, THREADS, kSmem, st>>>(a, stiles_per_bh, total_stiles);
         return cudaGetLastError();
     };
-    if (a.border) return launch(msda_bwd_scatter_kernel<T, LANES, LK, true, THREADS, ROUNDS, MAXROWS, NBP>);
-    return launch(msda_bwd_scatter_kernel<T, LANES, LK, false, THREADS, ROUNDS, MAXROWS, NBP>);
+    if (a.border) return launch(msda_bwd_scatter_kernel<T, LANES, LK, true, THREADS, ROUNDS, MAXHEADS, NBP>);
+    return launch(msda_bwd_scatter_kernel<T, LANES, LK, false, THREADS, ROUNDS, MAXHEADS, NBP>);
 }
 
 // grad_img only (a.gimg = fp32 accumulation image, already zero-filled).  cudaErrorNotSupported -> caller falls back.
 cudaError_t launch_backward_scatter(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st) {
-    if (a.LK != 16 || a.L > 16 || a.D != 32) return cudaErrorNotSupported;
+    if (a.LK != 16 || a.L > 8 || a.D != 32) return cudaErrorNotSupported;
     const unsigned long long tiles = (unsigned long long)a.B * a.H * a.Q;
     if (tiles >= (1ull << 31) || (unsigned long long)a.Npix >= (1ull << 23)) return cudaErrorNotSupported;
     if (dtype == 0) return launch_scatter_t<float, 8, 16>(a, sm_count, st);

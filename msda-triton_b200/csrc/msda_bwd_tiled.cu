@@ -359,9 +359,9 @@ cudaError_t launch_backward_tiled(const KernelArgs &a, int dtype, int sm_count, 
     }
     // grad_img ONLY (points / weights do not require grad): no pyramid gathers are needed at all, and the scatter-only
     // kernel with in-CTA binning is the faster way to produce it (bench shape: 0.29 ms versus 0.45 ms) -- provided there
-    // are enough 512-query super-tiles to fill the machine.
+    // are enough 384-query super-tiles to fill the machine.
     if (a.flags == kNeedImg && dtype == 0 && a.D == 32 &&
-        (long long)a.B * a.H * ((a.Q + 511) / 512) >= 2LL * sm_count) {
+        (long long)a.B * a.H * ((a.Q + 383) / 384) >= 2LL * sm_count) {
         const cudaError_t e = launch_backward_scatter(a, dtype, sm_count, st);
         if (e != cudaErrorNotSupported) return e;
     }
