@@ -265,39 +265,31 @@ int msda_backward(void *grad_img, void *grad_points, void *grad_weights, const v
     int vec = pick_vec(prob, {img, grad_out});
     while (vec > 1 && need_img && !aligned(accum, vec * acc_es > 16 ? 16 : vec * acc_es)) vec >>= 1;
 
-    msda::KernelArgs a;
-    fill_args(a, prob, vec);
-    a.img = img;
-    a.shapes = reinterpret_cast<const long long *>(img_shapes);
-    a.pts = sampling_points;
-    a.aw = attention_weights;
-    a.gout = grad_out;
-    a.gimg = accum;
-    a.gpts = grad_points;
-    a.gaw = grad_weights;
-    a.flags = flags & MSDA_BWD_NEED_ALL;
+    // kernel arguments for a given lane vector width
+    auto bind = [&](int v) {
+        msda::KernelArgs k;
+        fill_args(k, prob, v);
+        k.img = img;
+        k.shapes = reinterpret_cast<const long long *>(img_shapes);
+        k.pts = sampling_points;
+        k.aw = attention_weights;
+        k.gout = grad_out;
+        k.gimg = accum;
+        k.gpts = grad_points;
+        k.gaw = grad_weights;
+        k.flags = flags & MSDA_BWD_NEED_ALL;
+        return k;
+    };
 
     cudaError_t e = cudaErrorNotSupported;
     const bool tiled_ok = !force_generic() && vec * es == 16 && aligned(sampling_points, 16) &&
                           aligned(attention_weights, 8) && aligned(grad_points, 16) && aligned(grad_weights, 8) &&
                           aligned(accum, 16);
-    if (tiled_ok) e = msda::launch_backward_tiled(a, prob->dtype, dev.sm_count, st);
+    if (tiled_ok) e = msda::launch_backward_tiled(bind(vec), prob->dtype, dev.sm_count, st);
     if (e == cudaErrorNotSupported) {
         // generic kernel, 16-bit storage: lanes of 4 channels make every red.v4 a whole, contiguous 16 bytes
-        if (staged && vec > 4) {
-            vec = 4;
-            fill_args(a, prob, vec);
-            a.img = img;
-            a.shapes = reinterpret_cast<const long long *>(img_shapes);
-            a.pts = sampling_points;
-            a.aw = attention_weights;
-            a.gout = grad_out;
-            a.gimg = accum;
-            a.gpts = grad_points;
-            a.gaw = grad_weights;
-            a.flags = flags & MSDA_BWD_NEED_ALL;
-        }
-        e = msda::launch_backward_generic(a, prob->dtype, vec, dev.sm_count, st);
+        if (staged && vec > 4) vec = 4;
+        e = msda::launch_backward_generic(bind(vec), prob->dtype, vec, dev.sm_count, st);
     }
     if (e != cudaSuccess) return fail_cuda(e, "msda_backward launch");
 

@@ -76,17 +76,6 @@ def _shapes_i64(img_shapes: torch.Tensor) -> torch.Tensor:
     return img_shapes.contiguous()
 
 
-def _maybe_validate_shapes(shapes: torch.Tensor, num_pixels: int) -> None:
-    """Like the reference (frontend.py:71-105), the hot path never checks that sum(h*w) equals the pyramid length --
-    doing so needs a device->host sync.  MSDA_B200_VALIDATE=1 turns the check on (debugging aid): the level table is
-    built on the device by the library and read back."""
-    if os.environ.get("MSDA_B200_VALIDATE", "0") == "0":
-        return
-    table = level_table(shapes, num_pixels).cpu()
-    if int(table[-1, 2]) != 1:
-        raise ValueError(f"img_shapes describe {int(table[-1, 0])} pixels but img has {num_pixels}.")
-
-
 def _stream_ptr() -> ctypes.c_void_p:
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -230,6 +219,18 @@ def level_table(img_shapes: torch.Tensor, num_pixels: int) -> torch.Tensor:
         rc = _lib.get_lib().msda_level_table(_ptr(table), _ptr(shapes), L, int(num_pixels), _stream_ptr())
     _lib.check(rc, "msda_level_table")
     return table
+
+
+def _maybe_validate_shapes(shapes: torch.Tensor, num_pixels: int) -> None:
+    """Like the reference (frontend.py:71-105), the hot path never checks that sum(h*w) equals the pyramid length --
+    doing so needs a device->host sync.  MSDA_B200_VALIDATE=1 turns the check on (debugging aid): the level table is
+    built on the device by the library and read back."""
+    if os.environ.get("MSDA_B200_VALIDATE", "0") == "0":
+        return
+    table = level_table(shapes, num_pixels).cpu()
+    if int(table[-1, 2]) != 1:
+        raise ValueError(f"img_shapes describe {int(table[-1, 0])} pixels but img has {num_pixels}.")
+
 
 
 # The reference's names for this layer (kernels.py:351, :556) resolve to the CUDA implementation.
