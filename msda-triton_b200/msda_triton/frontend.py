@@ -178,21 +178,24 @@ def multiscale_deformable_attention(
     padding_mode: PaddingMode,
     align_corners: bool,
 ) -> torch.Tensor:
-    """
-    Differentiable multiscale deformable attention function.
+    """Multiscale deformable attention (Deformable DETR, arXiv:2010.04159), differentiable in ``img``,
+    ``sampling_points`` and ``attention_weights``.
 
-    Args:
-        img (torch.Tensor): Flattened image pyramid tensor of shape `[batch_size, num_image, num_head, num_channel]`,
-            where `num_image=sum(h[i]*w[i] for i in range(levels))`.
-        img_shapes (torch.Tensor): Shapes of each pyramid level, tensor of shape `[num_levels, 2]`, (height, width) order.
-        sampling_points (torch.Tensor): Tensor of shape `[batch_size, num_queries, num_heads, num_levels, num_points, 2]`,
-            (x, y) order, normalized to [0, 1] with (0, 0) the top-left and (1, 1) the bottom-right corner.
-        attention_weights (torch.Tensor): Tensor of shape `[batch_size, num_queries, num_heads, num_levels, num_points]`.
-        padding_mode (Literal["border", "zeros"]): Out-of-bounds samples take the closest pixel (`border`) or 0 (`zeros`).
-        align_corners (bool): Grid alignment, as in `torch.nn.functional.grid_sample`.
+    Shapes (B batch, I pyramid pixels, H heads, C channels per head, N queries, L levels, P points per level):
 
-    Returns:
-        output (torch.Tensor): Output tensor of shape `[batch_size, num_queries, num_heads, num_channels]`.
+    * ``img``                ``[B, I, H, C]`` -- the levels of the feature pyramid flattened and concatenated along
+      ``I = sum(h_l * w_l)``.
+    * ``img_shapes``         ``[L, 2]`` integer tensor, one ``(height, width)`` row per level, same order as in ``img``.
+    * ``sampling_points``    ``[B, N, H, L, P, 2]`` -- ``(x, y)`` in units of the level size: ``(0, 0)`` is the top-left
+      and ``(1, 1)`` the bottom-right corner of every level; values outside ``[0, 1]`` are handled by ``padding_mode``.
+    * ``attention_weights``  ``[B, N, H, L, P]``.
+    * ``padding_mode``       ``"border"`` clamps out-of-range samples to the nearest pixel, ``"zeros"`` makes the
+      out-of-range bilinear corners contribute 0.
+    * ``align_corners``      same meaning as in ``torch.nn.functional.grid_sample``.
+
+    Returns ``[B, N, H, C]``: for every (batch, query, head) the attention-weighted sum of the ``L * P`` bilinear samples.
+
+    CUDA tensors run the hand-written sm_100a kernels; CPU tensors run the torch route.
     """
     if img.device.type == "cuda":
         if img_shapes.device != img.device:
@@ -207,24 +210,17 @@ def multiscale_deformable_attention(
 # Module
 # ---------------------------------------------------------------------------------------------------------------------
 class MultiscaleDeformableAttention(nn.Module):
-    """
-    Multiscale deformable attention module (Deformable DETR, https://arxiv.org/abs/2010.04159, Figure 2): input and
-    output projections around :func:`multiscale_deformable_attention`.
+    """Deformable-attention layer: query / pyramid / output projections around the MSDA operator (Figure 2 of
+    arXiv:2010.04159).
 
-    Constructor signature, attribute names and parameter names (``img_input_proj``, ``query_input_proj``,
-    ``query_output_proj``) match the reference module (frontend.py:199-223) so checkpoints load unchanged.
+    The constructor signature and the parameter names (``img_input_proj``, ``query_input_proj``,
+    ``query_output_proj``) are those of the reference module (frontend.py:199-223), so its checkpoints load with
+    ``strict=True``.
 
-    Args:
-        emb_dim (int): Feature dimension of inputs.
-        hidden_dim (int): Feature dimension to which to project. Must be divisible by `num_heads`.
-        num_levels (int): Number of feature levels of input images.
-        num_heads (int): Number of attention heads.
-        num_points (int): Number of sampling points per level.
-        padding_mode (Literal["border", "zeros"]): See :func:`multiscale_deformable_attention`.
-        align_corners (bool): See :func:`multiscale_deformable_attention`.
-
-    Raises:
-        ValueError: If `hidden_dim` is not divisible by `num_heads`.
+    ``emb_dim`` is the width of the inputs and of the output, ``hidden_dim`` the width the pyramid is projected to
+    (``hidden_dim // num_heads`` channels per head; a ``ValueError`` is raised when it is not a multiple of
+    ``num_heads``), ``num_levels`` / ``num_points`` the number of pyramid levels and of sampling points per level,
+    ``padding_mode`` / ``align_corners`` as in :func:`multiscale_deformable_attention`.
     """
 
     def __init__(
@@ -259,17 +255,10 @@ class MultiscaleDeformableAttention(nn.Module):
         queries: torch.Tensor,
         reference_points: torch.Tensor,
     ) -> torch.Tensor:
-        """
-        Args:
-            img: `[batch_size, num_image, emb_dim]` flattened pyramid.
-            img_shapes: `[num_levels, 2]` level shapes, (height, width).
-            queries: `[batch_size, num_queries, emb_dim]`.
-            reference_points: `[batch_size, num_queries, 2]` (x, y) or `[batch_size, num_queries, 4]` (cx, cy, w, h),
-                normalized to [0, 1].
-
-        Returns:
-            `[batch_size, num_queries, emb_dim]`.
-        """
+        """``img`` ``[B, I, emb_dim]`` is the flattened pyramid, ``img_shapes`` ``[L, 2]`` its ``(height, width)`` rows,
+        ``queries`` ``[B, N, emb_dim]``; ``reference_points`` is ``[B, N, 2]`` (an ``(x, y)`` anchor per query) or
+        ``[B, N, 4]`` (a ``(cx, cy, w, h)`` box per query), normalised like the sampling points.  Returns
+        ``[B, N, emb_dim]``."""
         batch, num_pixels, _ = img.shape
         num_queries = queries.shape[1]
         heads, levels, points = self.num_heads, self.num_levels, self.num_points
