@@ -434,6 +434,8 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"     # keep stdout to the one JSON line (NCCL prints its banner there)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from msda_triton import _lib, kernels as K
