@@ -7,8 +7,8 @@ The reference has no equivalent (its tensors are expected on the device already)
     H2D(chunk i+1)   ||   kernels(chunk i)   ||   D2H(chunk i-1)
 
 so a step costs about max(H2D, D2H) + one chunk of compute instead of H2D + compute + D2H (PCIe is full duplex).
-Chunks are whole images because ``grad_img`` couples all queries of one image.  Two sets of device staging buffers are
-allocated once per :class:`HostMsda` and used alternately.
+Chunks are whole images because ``grad_img`` couples all queries of one image.  Two sets of device staging and result buffers
+are allocated once per :class:`HostMsda` and used alternately; a call allocates nothing.
 """
 from __future__ import annotations
 
@@ -21,7 +21,8 @@ from . import kernels
 
 class HostMsda:
     def __init__(self, batch: int, num_pixels: int, heads: int, channels: int, queries: int, levels: int, points: int,
-                 dtype: torch.dtype = torch.float32, device: Optional[torch.device] = None, backward: bool = True):
+                 dtype: torch.dtype = torch.float32, device: Optional[torch.device] = None, backward: bool = True,
+                 chunks: Optional[int] = None):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         d = dict(dtype=dtype, device=self.device)
 
@@ -31,7 +32,13 @@ class HostMsda:
                 "pts": torch.empty((batch, queries, heads, levels, points, 2), **d),
                 "aw": torch.empty((batch, queries, heads, levels, points), **d),
                 "go": torch.empty((batch, queries, heads, channels), **d) if backward else None,
-                "free": None,   # event: the kernels that read this staging set have finished
+                # device-side results (copied out by the D2H stream; "drained" guards their reuse)
+                "out": torch.empty((batch, queries, heads, channels), **d),
+                "gimg": torch.empty((batch, num_pixels, heads, channels), **d) if backward else None,
+                "gpts": torch.empty((batch, queries, heads, levels, points, 2), **d) if backward else None,
+                "gaw": torch.empty((batch, queries, heads, levels, points), **d) if backward else None,
+                "free": None,      # event: the kernels that read this staging set have finished
+                "drained": None,   # event: the D2H copies out of this set's result buffers have finished
             }
 
         # two staging sets: the H2D copies of call i+1 never wait for the kernels of call i
@@ -39,6 +46,10 @@ class HostMsda:
         self._turn = 0
         self.batch = batch
         self.backward = backward
+        # images per chunk: more chunks shorten the latency of ONE call (copy/compute overlap inside the call), fewer
+        # chunks mean fewer, larger copies, which is what sustained back-to-back calls want (they overlap across calls)
+        n_chunks = batch if chunks is None else max(1, min(int(chunks), batch))
+        self._bounds = [(batch * c // n_chunks, batch * (c + 1) // n_chunks) for c in range(n_chunks)]
         self.h2d = torch.cuda.Stream(self.device)
         self.d2h = torch.cuda.Stream(self.device)
 
@@ -66,9 +77,11 @@ class HostMsda:
         # may still be in flight, so back-to-back calls overlap this call's H2D with earlier D2H (PCIe is full duplex).
         if st["free"] is not None:
             self.h2d.wait_event(st["free"])
+        if st["drained"] is not None:
+            cur.wait_event(st["drained"])   # the kernels below overwrite this set's result buffers
         needs = (img_grad is not None, sampling_points_grad is not None, attention_weights_grad is not None)
-        for b in range(self.batch):
-            sl = slice(b, b + 1)
+        for lo, hi in self._bounds:
+            sl = slice(lo, hi)
             with torch.cuda.stream(self.h2d):
                 st["img"][sl].copy_(img[sl], non_blocking=True)
                 st["pts"][sl].copy_(sampling_points[sl], non_blocking=True)
@@ -78,12 +91,13 @@ class HostMsda:
                 ready = self.h2d.record_event()
             cur.wait_event(ready)
             o = kernels.b200_multi_scale_deformable_attention_fwd(
-                st["img"][sl], img_shapes_dev, st["pts"][sl], st["aw"][sl], padding_mode, align_corners)
+                st["img"][sl], img_shapes_dev, st["pts"][sl], st["aw"][sl], padding_mode, align_corners,
+                out=st["out"][sl])
             grads = (None, None, None)
             if do_bwd and any(needs):
                 grads = kernels.b200_multi_scale_deformable_attention_bwd(
                     st["go"][sl], st["img"][sl], img_shapes_dev, st["pts"][sl], st["aw"][sl], padding_mode, align_corners,
-                    needs=needs, deterministic=deterministic)
+                    needs=needs, deterministic=deterministic, grads=(st["gimg"][sl], st["gpts"][sl], st["gaw"][sl]))
             done = cur.record_event()
             self.d2h.wait_event(done)
             with torch.cuda.stream(self.d2h):
@@ -91,7 +105,7 @@ class HostMsda:
                                  (attention_weights_grad, grads[2])):
                     if dst is not None and src is not None:
                         dst[sl].copy_(src, non_blocking=True)
-                        src.record_stream(self.d2h)
+        st["drained"] = self.d2h.record_event()
         st["free"] = cur.record_event()
         return out
 

@@ -51,6 +51,13 @@ def _dense(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
+def _check_buffer(buf: torch.Tensor, shape, like: torch.Tensor, what: str) -> None:
+    if tuple(buf.shape) != tuple(shape) or buf.dtype != like.dtype or buf.device != like.device \
+            or not buf.is_contiguous() or buf.data_ptr() % 16 != 0:
+        raise ValueError(f"`{what}` buffer must be a contiguous, 16-byte aligned {tuple(shape)} {like.dtype} tensor on "
+                         f"{like.device}.")
+
+
 def _problem(img, img_shapes, pts, aw, padding_mode, align_corners) -> _lib.MsdaProblem:
     if padding_mode not in _PAD_CODE:
         raise ValueError(f"`padding_mode` should be 'border' or 'zeros', but got {padding_mode!r}.")
@@ -91,13 +98,18 @@ def b200_multi_scale_deformable_attention_fwd(
     attention_weights: torch.Tensor,
     padding_mode: Literal["border", "zeros"],
     align_corners: bool,
+    out: Optional[torch.Tensor] = None,
 ) -> torch.Tensor:
-    """out[b,q,h,:] = sum_{l,k} w[b,q,h,l,k] * bilinear(img_l[b,:,h,:], p[b,q,h,l,k]); out dtype = img dtype."""
+    """out[b,q,h,:] = sum_{l,k} w[b,q,h,l,k] * bilinear(img_l[b,:,h,:], p[b,q,h,l,k]); out dtype = img dtype.
+    ``out`` may be a preallocated contiguous ``[B, N, H, C]`` tensor (no allocation on the call path then)."""
     img, pts, aw = _dense(img), _dense(sampling_points), _dense(attention_weights)
     shapes = _shapes_i64(img_shapes)
     prob = _problem(img, shapes, pts, aw, padding_mode, align_corners)
     _maybe_validate_shapes(shapes, prob.Npix)
-    out = torch.empty((prob.B, prob.Q, prob.H, prob.D), dtype=img.dtype, device=img.device)
+    if out is None:
+        out = torch.empty((prob.B, prob.Q, prob.H, prob.D), dtype=img.dtype, device=img.device)
+    else:
+        _check_buffer(out, (prob.B, prob.Q, prob.H, prob.D), img, "out")
     with torch.cuda.device_of(img):
         rc = _lib.get_lib().msda_forward(_ptr(out), _ptr(img), _ptr(shapes), _ptr(pts), _ptr(aw), ctypes.byref(prob),
                                    _stream_ptr())
@@ -115,8 +127,10 @@ def b200_multi_scale_deformable_attention_bwd(
     align_corners: bool,
     needs: Sequence[bool] = (True, True, True),
     deterministic: Optional[bool] = None,
+    grads: Optional[Sequence[Optional[torch.Tensor]]] = None,
 ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor], Optional[torch.Tensor]]:
-    """Returns (img_grad, sampling_points_grad, attention_weights_grad); entries not in ``needs`` are None."""
+    """Returns (img_grad, sampling_points_grad, attention_weights_grad); entries not in ``needs`` are None.
+    ``grads`` may hold preallocated contiguous buffers for the three gradients (used where ``needs`` asks for them)."""
     img, pts, aw = _dense(img), _dense(sampling_points), _dense(attention_weights)
     shapes = _shapes_i64(img_shapes)
     prob = _problem(img, shapes, pts, aw, padding_mode, align_corners)
@@ -129,9 +143,19 @@ def b200_multi_scale_deformable_attention_bwd(
         deterministic = is_deterministic()
     if deterministic and need_img:
         flags |= _lib.BWD_DETERMINISTIC
-    gimg = torch.empty(img.shape, dtype=img.dtype, device=img.device) if need_img else None
-    gpts = torch.empty(pts.shape, dtype=pts.dtype, device=img.device) if need_pts else None
-    gaw = torch.empty(aw.shape, dtype=aw.dtype, device=img.device) if need_aw else None
+    pre = tuple(grads) if grads is not None else (None, None, None)
+
+    def buffer(need, given, like, what):
+        if not need:
+            return None
+        if given is None:
+            return torch.empty(like.shape, dtype=like.dtype, device=img.device)
+        _check_buffer(given, tuple(like.shape), img, what)
+        return given
+
+    gimg = buffer(need_img, pre[0], img, "img_grad")
+    gpts = buffer(need_pts, pre[1], pts, "sampling_points_grad")
+    gaw = buffer(need_aw, pre[2], aw, "attention_weights_grad")
     with torch.cuda.device_of(img):
         ws_bytes = int(_lib.get_lib().msda_backward_workspace_bytes(ctypes.byref(prob), flags))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=img.device) if ws_bytes else None
