@@ -147,3 +147,23 @@ def test_module_matches_reference_module_golden_cpu(name):
     from util import check_module_against_golden, load_module_golden
     g, module, inputs, shapes = load_module_golden(GOLDEN / f"{name}.npz")
     check_module_against_golden(g, module, inputs, shapes, rtol=1e-9, atol_scale=1e-11)
+
+
+def test_bench_reference_arm_emits_contract_json():
+    """`bench.py --impl reference` (the reference's CPU route on the host cores) prints ONE JSON line with the keys the
+    driver reads -- needs no GPU."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "queries/s" and d["value"] > 0
+    for key in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data",
+                "config", "cpu_baseline", "e2e"):
+        assert key in d
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0

@@ -45,3 +45,28 @@ def test_random_problem_matches_oracle(seed):
     assert_close(to_np(out), ref_out, tol[0], tol[1] * max(1.0, np.abs(ref_out).max()), what + " out")
     for t, r, n in ((gi, rgi, "grad_img"), (gp, rgp, "grad_points"), (ga, rga, "grad_weights")):
         assert_close(to_np(t), r, tol[2], tol[3] * max(1e-30, np.abs(r).max()), f"{what} {n}")
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_problem_16bit_storage(seed):
+    """Same sweep in fp16 / bf16 storage against the fp64 oracle on the rounded inputs.  out, grad_img and grad_weights
+    are continuous in the inputs: one storage rounding; grad_points may additionally flip floor cells for points that
+    the 16-bit quantisation put exactly on a pixel boundary (a small outlier budget)."""
+    from msda_triton import kernels as K_
+    from oracle import msda_oracle
+    rng = np.random.default_rng(5000 + seed)
+    B, Q, H, D, shapes, K, pm, ac, points = random_case(rng)
+    dtype = torch.bfloat16 if seed % 2 else torch.float16
+    img, s, pts, aw, go = make_inputs(B, Q, H, D, shapes, K, dtype=dtype, seed=seed, points=points, weights="softmax_lk")
+    dev = [t.cuda() for t in (img, s, pts, aw, go)]
+    out = K_.b200_multi_scale_deformable_attention_fwd(dev[0], dev[1], dev[2], dev[3], pm, ac)
+    gi, gp, ga = K_.b200_multi_scale_deformable_attention_bwd(dev[4], dev[0], dev[1], dev[2], dev[3], pm, ac)
+    ref_out = msda_oracle.forward(img, s, pts, aw, pm, ac)
+    rgi, rgp, rga = msda_oracle.backward(go, img, s, pts, aw, pm, ac)
+    eps = 2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -10
+    what = f"seed {seed}: B={B} Q={Q} H={H} D={D} shapes={shapes} K={K} {pm}/{ac} {points} {dtype}"
+    for t, r, n, budget in ((out, ref_out, "out", 0.0), (gi, rgi, "grad_img", 0.0), (ga, rga, "grad_weights", 0.0),
+                            (gp, rgp, "grad_points", 0.02)):
+        assert t.dtype == dtype
+        assert_close(to_np(t), r, eps, eps * 2e-2 * max(1e-30, np.abs(r).max()), f"{what} {n}",
+                     max_outliers=int(budget * r.size) + (2 if budget else 0))
