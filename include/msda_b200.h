@@ -126,7 +126,7 @@ int msda_backward(void *grad_img, void *grad_points, void *grad_weights, const v
  *   value  [B, Npix, H, D]        projected pyramid
  *   proj   [B, Q, H, L, K, 3]     query projection viewed as (offset x, offset y, attention logit) triples
  *   ref    [B, Q, ref_dim]        reference points, ref_dim = 2 or 4
- * msda_module_supported returns 1 when the fused kernels cover `prob` (fp32/fp16/bf16, D == 32, L*K == 16); otherwise
+ * msda_module_supported returns 1 when the fused kernels cover `prob` (fp32/fp16/bf16, D in {32, 64}, L*K == 16); otherwise
  * the caller composes the unfused pieces (softmax etc. + msda_forward).
  * Backward flags: MSDA_BWD_NEED_IMG -> grad_value, NEED_POINTS|NEED_WEIGHTS -> grad_proj, NEED_REF -> grad_ref.
  * grad_ref is an fp32 [B, Q, ref_dim] buffer regardless of the storage dtype; the library zero-fills it and grad_value.

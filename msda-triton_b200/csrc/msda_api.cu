@@ -304,7 +304,8 @@ int msda_backward(void *grad_img, void *grad_points, void *grad_weights, const v
 int msda_module_supported(const msda_problem *prob, int ref_dim) {
     if (validate(prob) != MSDA_OK) return 0;
     if (ref_dim != 2 && ref_dim != 4) return 0;
-    if (prob->dtype == MSDA_DTYPE_F64 || prob->D != 32 || prob->L * prob->K != 16 || prob->L > 8) return 0;
+    if (prob->dtype == MSDA_DTYPE_F64 || (prob->D != 32 && prob->D != 64) || prob->L * prob->K != 16 || prob->L > 8)
+        return 0;
     msda::KernelArgs a;
     fill_args(a, prob, 1);
     return msda::tiled_offsets_fit(a, dtype_size(prob->dtype)) ? 1 : 0;
@@ -315,7 +316,7 @@ int msda_module_forward(void *out, const void *value, const int64_t *img_shapes,
     int rc = validate(prob);
     if (rc != MSDA_OK) return rc;
     if (!msda_module_supported(prob, ref_dim))
-        return fail(MSDA_ERR_BAD_SHAPE, "msda_module_forward: unsupported problem (needs fp32/fp16/bf16, D == 32, "
+        return fail(MSDA_ERR_BAD_SHAPE, "msda_module_forward: unsupported problem (needs fp32/fp16/bf16, D in {32, 64}, "
                                         "L*K == 16, ref_dim 2 or 4); use msda_forward on materialised operands");
     if (prob->B == 0 || prob->Q == 0) return MSDA_OK;
     if (!out || !value || !img_shapes || !proj || !ref)

@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                         }
                         gtriple[3 * pp + 2] = op.wa[pp] * (part[3 * pp + 0] - dot);
                     }
-                    constexpr int E8 = 8 / (int)sizeof(T);
+                    constexpr int E8 = FusedChunk<T, PPL>::kElems;
                     T *__restrict__ gproj = static_cast<T *>(a.gproj) + ((size_t)tu.u * LK + j * PPL) * 3;
 #pragma unroll
                     for (int c = 0; c < 3 * PPL / E8; ++c) {
@@ -323,10 +323,16 @@ static cudaError_t launch_tiled_t(const KernelArgs &a, int sm_count, cudaStream_
 
 // Backward of the fused module core; same eligibility as launch_module_forward_tiled.
 cudaError_t launch_module_backward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st) {
-    if (a.LK != 16 || a.L > 8 || a.D != 32 || (a.ref_dim != 2 && a.ref_dim != 4)) return cudaErrorNotSupported;
-    if (dtype == 0) return launch_tiled_t<float, 8, 16, true>(a, sm_count, st);
-    if (dtype == 1) return launch_tiled_t<__half, 4, 16, true>(a, sm_count, st);
-    if (dtype == 2) return launch_tiled_t<__nv_bfloat16, 4, 16, true>(a, sm_count, st);
+    if (a.LK != 16 || a.L > 8 || (a.ref_dim != 2 && a.ref_dim != 4)) return cudaErrorNotSupported;
+    if (a.D == 32) {
+        if (dtype == 0) return launch_tiled_t<float, 8, 16, true>(a, sm_count, st);
+        if (dtype == 1) return launch_tiled_t<__half, 4, 16, true>(a, sm_count, st);
+        if (dtype == 2) return launch_tiled_t<__nv_bfloat16, 4, 16, true>(a, sm_count, st);
+    } else if (a.D == 64) {
+        if (dtype == 0) return launch_tiled_t<float, 16, 16, true>(a, sm_count, st);
+        if (dtype == 1) return launch_tiled_t<__half, 8, 16, true>(a, sm_count, st);
+        if (dtype == 2) return launch_tiled_t<__nv_bfloat16, 8, 16, true>(a, sm_count, st);
+    }
     return cudaErrorNotSupported;
 }
 

@@ -144,6 +144,13 @@ __device__ __forceinline__ void corner_offsets(unsigned off, unsigned pack, unsi
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kNeedRef = 16;   // msda_module_backward: grad of the reference points requested
 
+// Elements per aligned chunk of a lane's (offset x, offset y, logit) triples in the fused module core.
+template <typename T, int PPL> struct FusedChunk {
+    static constexpr int kBytes = ((3 * PPL * (int)sizeof(T)) % 8 == 0) ? 8 : 4;
+    static constexpr int kElems = kBytes / (int)sizeof(T);
+    static_assert(kElems >= 1 && (3 * PPL) % kElems == 0, "unsupported lane layout for the fused module core");
+};
+
 template <typename T, int PPL, bool FUSED> struct LaneOperands {
     float xy[2 * PPL];    // sampling points of this lane's PPL points (x, y)
     float wa[PPL];        // attention weights
@@ -179,8 +186,9 @@ __device__ __forceinline__ void load_operands(const KernelArgs &a, const TileUni
             }
         }
     } else {
-        constexpr int E8 = 8 / (int)sizeof(T);            // elements per 8-byte chunk
-        static_assert((3 * PPL) % E8 == 0, "fused operands are fetched in 8-byte chunks");
+        // a lane's 3*PPL elements start at a multiple of 3*PPL*sizeof(T) bytes: 8-byte chunks when that is a multiple
+        // of 8 (D = 32), else 4-byte chunks (D = 64: 12 bytes per lane)
+        constexpr int E8 = FusedChunk<T, PPL>::kElems;
         static_assert(!PADDED, "the fused module core is instantiated for exact L*K only");
         const T *__restrict__ proj = static_cast<const T *>(a.proj) + ((size_t)tu.u * LK + j * PPL) * 3;
 #pragma unroll

@@ -185,7 +185,7 @@ def _module_problem(value, img_shapes, proj, ref, padding_mode, align_corners) -
 
 
 def module_core_supported(value: torch.Tensor, proj: torch.Tensor, ref: torch.Tensor) -> bool:
-    """True when the fused kernels cover this problem (CUDA, fp32/fp16/bf16, head_dim 32, L*K == 16)."""
+    """True when the fused kernels cover this problem (CUDA, fp32/fp16/bf16, head_dim 32 or 64, L*K == 16)."""
     if not value.is_cuda or value.dtype not in (torch.float32, torch.float16, torch.bfloat16):
         return False
     if not (value.dtype == proj.dtype == ref.dtype) or proj.dim() != 6 or ref.shape[-1] not in (2, 4):

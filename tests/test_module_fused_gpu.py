@@ -29,10 +29,12 @@ def composed_reference(value, shapes, proj, ref, pm, ac):
 @pytest.mark.parametrize("coords", [2, 4])
 @pytest.mark.parametrize("pm,ac", list(itertools.product(("zeros", "border"), (False, True))))
 @pytest.mark.parametrize("pyramid", [BENCH_PYRAMID, [(25, 42), (13, 21), (7, 11), (4, 6)]], ids=["square", "rect"])
-def test_fused_core_matches_composed_fp64(coords, pm, ac, pyramid):
+@pytest.mark.parametrize("D", [32, 64])
+def test_fused_core_matches_composed_fp64(coords, pm, ac, pyramid, D):
+    from msda_triton import kernels
     from msda_triton.frontend import fused_module_core
     g = torch.Generator().manual_seed(31 + coords)
-    B, Q, H, D, L, K = 2, 333, 8, 32, 4, 4
+    B, Q, H, L, K = 2, 333, 8, 4, 4
     npix = sum(h * w for h, w in pyramid)
     value = torch.randn(B, npix, H, D, generator=g)
     proj = torch.randn(B, Q, H, L, K, 3, generator=g)
@@ -48,6 +50,7 @@ def test_fused_core_matches_composed_fp64(coords, pm, ac, pyramid):
     want.backward(go.double())
 
     x, y, z = (t.cuda().requires_grad_(True) for t in (value, proj, ref))
+    assert kernels.module_core_supported(x, y, z)
     got = fused_module_core(x, shapes.cuda(), y, z, pm, ac)
     got.backward(go.cuda())
     assert_close(to_np(got), to_np(want), 1e-4, 1e-5, "out")
@@ -58,7 +61,8 @@ def test_fused_core_matches_composed_fp64(coords, pm, ac, pyramid):
 
 @pytest.mark.parametrize("coords", [2, 4])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
-def test_module_fused_equals_composed_cuda(coords, dtype):
+@pytest.mark.parametrize("hidden", [256, 512], ids=["d32", "d64"])
+def test_module_fused_equals_composed_cuda(coords, dtype, hidden):
     """Same module, same weights: fused fast path vs the composed CUDA path (MSDA_B200_FUSED_MODULE=0) run in fp32.
     (For bf16 the composed path itself rounds the sampling points to bf16 -- a quarter of a pixel on a 64-pixel level --
     so the yardstick is the fp32 composed module on the same bf16-rounded weights and inputs.)"""
@@ -71,7 +75,7 @@ def test_module_fused_equals_composed_cuda(coords, dtype):
     queries = torch.randn(2, 200, emb).to("cuda", dtype)
     ref_pts = (torch.rand(2, 200, coords) * 0.8 + 0.1).to("cuda", dtype)
     shapes = torch.tensor(BENCH_PYRAMID, device="cuda")
-    module = MultiscaleDeformableAttention(emb, emb, levels, heads, points, "border", True).to("cuda", dtype)
+    module = MultiscaleDeformableAttention(emb, hidden, levels, heads, points, "border", True).to("cuda", dtype)
     reference = copy.deepcopy(module).float()
 
     def run(mod, cast, fused):
@@ -100,14 +104,15 @@ def test_module_fused_equals_composed_cuda(coords, dtype):
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
 @pytest.mark.parametrize("coords", [2, 4])
-def test_fused_core_16bit_storage(dtype, coords):
+@pytest.mark.parametrize("D", [32, 64])
+def test_fused_core_16bit_storage(dtype, coords, D):
     """16-bit storage, fp32 compute: out and grad_value (continuous in the inputs) within one storage rounding of the
     fp64 composed reference on the same rounded inputs; offset / reference gradients within the same bound except for
     the boundary-tie outliers described above (< 2 % of the offset gradients; each reference-point gradient sums 128 of
     them, so up to 10 % of those may contain one)."""
     from msda_triton.frontend import fused_module_core
     g = torch.Generator().manual_seed(5)
-    B, Q, H, D, L, K = 2, 333, 8, 32, 4, 4
+    B, Q, H, L, K = 2, 333, 8, 4, 4
     npix = sum(h * w for h, w in BENCH_PYRAMID)
     value = torch.randn(B, npix, H, D, generator=g).to(dtype)
     proj = torch.randn(B, Q, H, L, K, 3, generator=g)
