@@ -52,10 +52,13 @@ template <int N, int STEP> __device__ __forceinline__ void transpose_reduce(floa
 // ref_wh/2K scaling) and accumulates grad of the reference points with a handful of scalar atomics per unit.
 // VEC = channels per lane: 16 bytes per lane by default; the non-fused 16-bit-storage backward runs 8 lanes x 4
 // channels (8-byte gathers) so that its fp32 row adds have the same full-sector shape as the fp32 kernel's.
-// PADDED: see the forward kernel -- a.LK <= LK real points, dead slots skipped warp-uniformly, per-point stores.
-template <typename T, int LANES, int LK, bool BORDER, int NB, int THREADS, bool FUSED, int VEC, bool PADDED>
+// PADDED: see the forward kernel -- a.LK <= LK real points, per-point loads / stores; dead slots are gathered (point
+// (0,0), weight 0) but add nothing.
+// SPLIT: units with more than LK points run as `subs` sub-units of LK slots each (decode_tile in msda_tiled.cuh).
+template <typename T, int LANES, int LK, bool BORDER, int NB, int THREADS, bool FUSED, int VEC, bool PADDED,
+          bool SPLIT>
 __global__ void __launch_bounds__(THREADS, 1)
-    msda_bwd_tiled_kernel(const KernelArgs a, const WaveSchedule ws) {
+    msda_bwd_tiled_kernel(const KernelArgs a, const WaveSchedule ws, const int subs_arg) {
     using Cfg = TiledCfg<T, LANES, LK>;
     constexpr int G = Cfg::G, PPL = Cfg::PPL;
     using Raw = typename RawSlice<VEC * (int)sizeof(T)>::type;
@@ -79,6 +82,8 @@ __global__ void __launch_bounds__(THREADS, 1)
     constexpr unsigned kAccScale = sizeof(float) / sizeof(T);  // accumulation row bytes / storage row bytes
 
     const int tiles_per_bh = ws.tiles_per_bh;
+    const int subs = SPLIT ? subs_arg : 1;
+    static_assert(!(SPLIT && FUSED), "the fused module core is instantiated for L*K == 16 only");
     for (int wave = 0; wave < ws.waves; ++wave) {
     int t_begin, t_end;
     wave_range(ws, wave, blockIdx.x, gridDim.x, t_begin, t_end);
@@ -86,7 +91,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     int tile = t_begin + warp;
     if (tile >= t_end) continue;
 
-    TileUnit tu = decode_tile(tile, tiles_per_bh, g, G, a);
+    TileUnit tu = decode_tile(tile, tiles_per_bh, g, G, a, subs, LK);
     LaneOperands<T, PPL, FUSED> op;
     float go[VEC];
     load_operands<T, LANES, LK, FUSED, PADDED>(a, tu, j, op);
@@ -95,7 +100,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     for (; tile < t_end; tile += nwarps) {
         const int tile_n = tile + nwarps;
         const bool has_next = tile_n < t_end;
-        const TileUnit tu_n = decode_tile(has_next ? tile_n : tile, tiles_per_bh, g, G, a);
+        const TileUnit tu_n = decode_tile(has_next ? tile_n : tile, tiles_per_bh, g, G, a, subs, LK);
         LaneOperands<T, PPL, FUSED> op_n;
         float go_n[VEC];
         load_operands<T, LANES, LK, FUSED, PADDED>(a, tu_n, j, op_n);
@@ -109,12 +114,13 @@ __global__ void __launch_bounds__(THREADS, 1)
         unsigned char *__restrict__ gimg_base = reinterpret_cast<unsigned char *>(gimg + tu.bh_off + j * 4);
         // padding queries of the last tile shadow a real query: their image contributions are scaled to zero
         const float live_scale = tu.live ? 1.0f : 0.0f;
+        const int p0 = SPLIT ? tu.p0 : 0;   // first point of this tile's sub-unit
 
         TileTap tap[PPL];
         float sx[PPL], sy[PPL];
 #pragma unroll
         for (int pp = 0; pp < PPL; ++pp) {
-            const Level lv = s_lv[slot_level(j * PPL + pp, a)];
+            const Level lv = s_lv[slot_level(p0 + j * PPL + pp, a)];
             tap[pp] = resolve_tap<BORDER>(op.xy[2 * pp], op.xy[2 * pp + 1], lv, align, row_bytes);
             sx[pp] = align ? (float)(lv.w - 1) : (float)lv.w;
             sy[pp] = align ? (float)(lv.h - 1) : (float)lv.h;
@@ -134,7 +140,9 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll
                 for (int n = 0; n < NB; ++n) {
                     const int src = jj0 + n;
-                    if (PADDED && src * PPL + pp >= a.LK) continue;   // dead slot (warp-uniform)
+                    // dead slots of a padded instantiation carry point (0,0) with weight 0: they are gathered like any
+                    // other (one in-range row, L1 hits) so that the NB x 4 loads stay one branch-free batch, and only
+                    // their row adds are skipped
                     const unsigned off = __shfl_sync(0xffffffffu, tap[pp].off, src, LANES);
                     const unsigned pack = __shfl_sync(0xffffffffu, tap[pp].pack, src, LANES);
                     fx[n] = __shfl_sync(0xffffffffu, tap[pp].dx, src, LANES);
@@ -148,11 +156,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                 }
 #pragma unroll
                 for (int n = 0; n < NB; ++n) {
-                    if (PADDED && (jj0 + n) * PPL + pp >= a.LK) {
-                        const int dead = (jj0 + n) * PPL + pp;
-                        part[3 * dead + 0] = part[3 * dead + 1] = part[3 * dead + 2] = 0.0f;
-                        continue;
-                    }
+                    const bool alive = !PADDED || p0 + (jj0 + n) * PPL + pp < a.LK;
                     const float dx = fx[n], dy = fy[n];
                     float bw[4];  // bilinear weights of corners 00, 01, 10, 11
                     bw[1] = (1.0f - dy) * dx;
@@ -174,7 +178,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll
                             for (int e = 0; e < VEC; ++e) gv[e] = go[e] * s;
                             float *dst = reinterpret_cast<float *>(gimg_base + (size_t)o[n][c] * kAccScale);
-                            if (BORDER || ((msk[n] >> c) & 1u)) red_add_row<VEC, LANES>(dst, gv);
+                            if (alive && (BORDER || ((msk[n] >> c) & 1u))) red_add_row<VEC, LANES>(dst, gv);
                         }
                     }
                     const int pidx = (jj0 + n) * PPL + pp;
@@ -197,7 +201,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                         float gw[PPL];
 #pragma unroll
                         for (int pp = 0; pp < PPL; ++pp) gw[pp] = part[3 * pp + 0];
-                        store_vec_stream<T, PPL>(gaw_u + j * PPL, gw);
+                        store_vec_stream<T, PPL>(gaw_u + p0 + j * PPL, gw);
                     }
                     if (need_pts) {
                         float gp[2 * PPL];
@@ -206,12 +210,12 @@ __global__ void __launch_bounds__(THREADS, 1)
                             gp[2 * pp + 0] = part[3 * pp + 1] * (op.wa[pp] * sx[pp]);
                             gp[2 * pp + 1] = part[3 * pp + 2] * (op.wa[pp] * sy[pp]);
                         }
-                        store_vec_stream<T, 2 * PPL>(gpts_u + j * PPL * 2, gp);
+                        store_vec_stream<T, 2 * PPL>(gpts_u + (p0 + j * PPL) * 2, gp);
                     }
                 } else {
 #pragma unroll
                     for (int pp = 0; pp < PPL; ++pp) {
-                        const int p = j * PPL + pp;
+                        const int p = p0 + j * PPL + pp;
                         if (p < a.LK) {
                             if (need_aw) {
                                 const float gw1[1] = {part[3 * pp + 0]};
@@ -301,12 +305,13 @@ __global__ void __launch_bounds__(THREADS, 1)
 }
 
 
-template <typename T, int LANES, int LK, bool FUSED = false, int VEC = 16 / (int)sizeof(T), bool PADDED = false>
-static cudaError_t launch_tiled_t(const KernelArgs &a, int sm_count, cudaStream_t st) {
+template <typename T, int LANES, int LK, bool FUSED = false, int VEC = 16 / (int)sizeof(T), bool PADDED = false,
+          bool SPLIT = false>
+static cudaError_t launch_tiled_t(const KernelArgs &a, int sm_count, cudaStream_t st, int subs = 1) {
     constexpr int THREADS = 512, NB = 2;
     constexpr int G = TiledCfg<T, LANES, LK>::G;
-    if (!tiled_offsets_fit(a, sizeof(T))) return cudaErrorNotSupported;
-    const int tiles_per_bh = (a.Q + G - 1) / G;
+    if (!tiled_offsets_fit(a, sizeof(T), subs)) return cudaErrorNotSupported;
+    const int tiles_per_bh = subs * ((a.Q + G - 1) / G);
     const int total_tiles = a.B * a.H * tiles_per_bh;
     const int warps = THREADS / 32;
     const int want = (total_tiles + warps - 1) / warps;
@@ -315,10 +320,34 @@ static cudaError_t launch_tiled_t(const KernelArgs &a, int sm_count, cudaStream_
     const size_t per_slice_factor = (a.flags & kNeedImg) ? sizeof(T) + sizeof(float) : sizeof(T);
     const WaveSchedule ws = make_wave_schedule(a, tiles_per_bh, per_slice_factor, kBwdL2Budget);
     if (a.border)
-        msda_bwd_tiled_kernel<T, LANES, LK, true, NB, THREADS, FUSED, VEC, PADDED><<<grid, THREADS, 0, st>>>(a, ws);
+        msda_bwd_tiled_kernel<T, LANES, LK, true, NB, THREADS, FUSED, VEC, PADDED, SPLIT>
+            <<<grid, THREADS, 0, st>>>(a, ws, subs);
     else
-        msda_bwd_tiled_kernel<T, LANES, LK, false, NB, THREADS, FUSED, VEC, PADDED><<<grid, THREADS, 0, st>>>(a, ws);
+        msda_bwd_tiled_kernel<T, LANES, LK, false, NB, THREADS, FUSED, VEC, PADDED, SPLIT>
+            <<<grid, THREADS, 0, st>>>(a, ws, subs);
     return cudaGetLastError();
+}
+
+// More than 16 sampling points per unit (5-level pyramids, K = 8): sub-units of SLOTS points, see decode_tile().
+template <typename T, int LANES, int SLOTS, bool PADDED>
+static cudaError_t launch_split_t(const KernelArgs &a, int sm_count, cudaStream_t st) {
+    const int subs = (a.LK + SLOTS - 1) / SLOTS;
+    return launch_tiled_t<T, LANES, SLOTS, false, 4, PADDED, true>(a, sm_count, st, subs);
+}
+
+template <typename T> static cudaError_t launch_split(const KernelArgs &a, int sm_count, cudaStream_t st) {
+    if (a.D == 32) {
+        if (a.LK % 16 == 0) return launch_split_t<T, 8, 16, false>(a, sm_count, st);
+        if (a.LK % 8 == 0) return launch_split_t<T, 8, 8, false>(a, sm_count, st);
+        // ragged: the slot count that wastes fewer dead slots (20 points: 3 x 8 rather than 2 x 16; 0.91 vs 1.10 ms)
+        const int dead16 = (a.LK + 15) / 16 * 16 - a.LK, dead8 = (a.LK + 7) / 8 * 8 - a.LK;
+        bool use8 = dead8 <= dead16;   // tie: 8 slots measured faster (28 points: 0.89 vs 0.94 ms)
+        if (const char *e = std::getenv("MSDA_B200_SPLIT_SLOTS")) use8 = std::atoi(e) == 8;   // tuning knob
+        if (use8) return launch_split_t<T, 8, 8, true>(a, sm_count, st);
+        return launch_split_t<T, 8, 16, true>(a, sm_count, st);
+    }
+    if (a.D == 64 && a.LK % 16 == 0) return launch_split_t<T, 16, 16, false>(a, sm_count, st);
+    return cudaErrorNotSupported;
 }
 
 // Backward of the fused module core; same eligibility as launch_module_forward_tiled.
@@ -339,13 +368,21 @@ cudaError_t launch_module_backward_tiled(const KernelArgs &a, int dtype, int sm_
 // MSDA_B200_BWD_SPLIT=1 selects the experimental split backward: K1 = this file's kernel without grad_img, K2 =
 // msda_bwd_scatter.cu (grad_img alone, binned in shared memory).  Measured 0.19 + 0.29 ms on the bench shape versus
 // 0.47 ms fused (profiles/r1_ncu_summary.md section 4), so it is opt-in.
+constexpr int kMaxSplitPoints = 128;
+
 static bool split_backward_enabled() {
     const char *e = std::getenv("MSDA_B200_BWD_SPLIT");
     return e && e[0] && e[0] != '0';
 }
 
 cudaError_t launch_backward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st) {
-    if (a.L > 8 || a.LK > 16) return cudaErrorNotSupported;   // 3*L*K partials live in registers: up to 16 points
+    if (a.L > 8 || a.LK > kMaxSplitPoints) return cudaErrorNotSupported;
+    if (a.LK > 16) {   // 3*L*K partials live in registers, 16 points at a time: larger units run as sub-units
+        if (dtype == 0) return launch_split<float>(a, sm_count, st);
+        if (dtype == 1) return launch_split<__half>(a, sm_count, st);
+        if (dtype == 2) return launch_split<__nv_bfloat16>(a, sm_count, st);
+        return cudaErrorNotSupported;
+    }
     if (a.LK != 16) {
         if (a.D != 32) return cudaErrorNotSupported;
         if (a.LK == 8) {

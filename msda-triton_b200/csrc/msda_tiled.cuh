@@ -30,9 +30,9 @@ template <typename T, int LANES, int LK> struct TiledCfg {
 };
 
 // Host-side eligibility of the 32-bit offset arithmetic below (shapes live on the device, so bound w by Npix).
-inline bool tiled_offsets_fit(const KernelArgs &a, size_t elem_size) {
+inline bool tiled_offsets_fit(const KernelArgs &a, size_t elem_size, int subs = 1) {
     const unsigned long long row_bytes = (unsigned long long)a.H * a.D * elem_size;
-    const unsigned long long tiles = (unsigned long long)a.B * a.H * a.Q;  // upper bound on the warp-tile count
+    const unsigned long long tiles = (unsigned long long)a.B * a.H * a.Q * subs;  // upper bound on the warp-tile count
     return (unsigned long long)a.Npix * row_bytes < (1ull << 28) && tiles < (1ull << 31);
 }
 
@@ -83,17 +83,30 @@ __device__ __forceinline__ void wave_range(const WaveSchedule &w, int wave, int 
 struct TileUnit {
     long long u;      // unit index (b*Q + q)*H + h of the (possibly shadowed) query
     size_t bh_off;    // element offset of img[b, 0, h, 0]
+    int p0;           // first sampling point of this tile's sub-unit (0 unless the unit is split, see below)
     bool live;        // false for the padding queries of the last tile of a (b,h)
 };
 
-__device__ __forceinline__ TileUnit decode_tile(int tile, int tiles_per_bh, int g, int G, const KernelArgs &a) {
+// `subs` > 1 (backward only): a unit with more sampling points than the instantiation has slots is processed as
+// `subs` SUB-UNITS of `slots` points each -- the backward has no reduction across points, so the sub-units only share
+// the grad_out row.  The tiles of a (b,h) slice are ordered sub-unit-major (all queries of sub-unit 0, then sub-unit 1,
+// ...), which keeps the sub-unit -- hence the set of dead slots of a padded instantiation -- uniform across a warp.
+__device__ __forceinline__ TileUnit decode_tile(int tile, int tiles_per_bh, int g, int G, const KernelArgs &a,
+                                                int subs = 1, int slots = 0) {
     const int bh = tile / tiles_per_bh;
-    const int qt = tile - bh * tiles_per_bh;
+    int qt = tile - bh * tiles_per_bh;
+    int sub = 0;
+    if (subs > 1) {
+        const int tiles_per_sub = tiles_per_bh / subs;
+        sub = qt / tiles_per_sub;
+        qt -= sub * tiles_per_sub;
+    }
     const int b = bh / a.H;
     const int h = bh - b * a.H;
     const int q_raw = qt * G + g;
     TileUnit t;
     t.live = q_raw < a.Q;
+    t.p0 = sub * slots;
     const int q = t.live ? q_raw : a.Q - 1;
     t.u = ((long long)b * a.Q + q) * a.H + h;
     t.bh_off = ((size_t)b * a.Npix * a.H + h) * a.D;
@@ -169,12 +182,12 @@ __device__ __forceinline__ void load_operands(const KernelArgs &a, const TileUni
         const T *__restrict__ pts = static_cast<const T *>(a.pts) + (size_t)tu.u * a.LK * 2;
         const T *__restrict__ aw = static_cast<const T *>(a.aw) + (size_t)tu.u * a.LK;
         if constexpr (!PADDED) {
-            load_vec_stream<T, 2 * PPL>(pts + j * PPL * 2, op.xy);
-            load_vec_stream<T, PPL>(aw + j * PPL, op.wa);
+            load_vec_stream<T, 2 * PPL>(pts + (tu.p0 + j * PPL) * 2, op.xy);
+            load_vec_stream<T, PPL>(aw + tu.p0 + j * PPL, op.wa);
         } else {
 #pragma unroll
             for (int pp = 0; pp < PPL; ++pp) {
-                const int p = j * PPL + pp;
+                const int p = tu.p0 + j * PPL + pp;
                 float xy2[2] = {0.0f, 0.0f}, w1[1] = {0.0f};
                 if (p < a.LK) {
                     load_vec_stream<T, 2>(pts + 2 * p, xy2);

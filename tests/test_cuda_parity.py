@@ -113,6 +113,13 @@ CASES = {
     "lk4_one_level": (2, 350, 8, 32, [(17, 23)], 4, "wide", "softmax_lk"),            # padded 8
     "lk28_k7": (1, 222, 8, 32, BENCH_PYRAMID, 7, "wide", "softmax_lk"),               # padded 32 (forward)
     "lk12_rtdetr": (2, 300, 8, 32, [(40, 40), (20, 20), (10, 10)], 4, "unit", "softmax_lk"),  # padded 16 (L=3, K=4)
+    # backward with more than 16 points per unit: sub-units of 8 / 16 slots (forward: generic beyond 32 points)
+    "lk24_k8": (2, 301, 8, 32, [(40, 40), (20, 20), (10, 10)], 8, "wide", "softmax_lk"),      # 3 x 8 exact
+    "lk48_six_levels": (1, 203, 8, 32, [(32, 40), (16, 20), (8, 10), (4, 5), (2, 3), (1, 2)], 8, "wide", "softmax_lk"),
+    "lk30_k10": (1, 257, 8, 32, [(40, 40), (20, 20), (10, 10)], 10, "far", "softmax_lk"),     # 2 x 16, 2 dead slots
+    "lk36_k9": (1, 199, 8, 32, BENCH_PYRAMID, 9, "wide", "softmax_lk"),                       # 5 x 8, 4 dead slots
+    "lk64_d64": (1, 150, 4, 64, [(32, 40), (16, 20), (8, 10), (4, 5), (2, 3), (1, 2), (1, 1), (2, 2)], 8, "wide",
+                 "softmax_lk"),                                                               # 4 x 16, 16 lanes
 }
 
 
@@ -128,10 +135,11 @@ def test_oracle_parity(K, oracle, name, dtype, pm, ac):
 
 
 @pytest.mark.parametrize("pm,ac", MODES)
-def test_tuned_equals_generic(K, pm, ac):
+@pytest.mark.parametrize("Kp", [4, 8, 5], ids=["lk16", "lk32_split", "lk20_split_padded"])
+def test_tuned_equals_generic(K, pm, ac, Kp):
     """The tuned (persistent, (b,h)-major) kernels and the generic kernels implement the same arithmetic per corner;
     only summation order differs."""
-    img, s, pts, aw, go = make_inputs(2, 500, 8, 32, BENCH_PYRAMID, 4, seed=3, points="wide")
+    img, s, pts, aw, go = make_inputs(2, 500, 8, 32, BENCH_PYRAMID, Kp, seed=3, points="wide")
     tuned = run_cuda(K, img, s, pts, aw, go, pm, ac)
     os.environ["MSDA_B200_FORCE_GENERIC"] = "1"
     try:
@@ -153,7 +161,7 @@ def _bounds(dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
-@pytest.mark.parametrize("D,Kp", [(32, 4), (64, 4), (32, 3), (4, 8), (32, 2), (32, 1)])
+@pytest.mark.parametrize("D,Kp", [(32, 4), (64, 4), (32, 3), (4, 8), (32, 2), (32, 1), (32, 8), (32, 5), (64, 8)])
 @pytest.mark.parametrize("pm,ac", MODES)
 def test_16bit_storage_bounds(K, oracle, dtype, D, Kp, pm, ac):
     """16-bit STORAGE, fp32 compute: against the fp64 oracle evaluated on the same (already rounded) inputs every
