@@ -89,17 +89,20 @@ struct TileUnit {
 
 // `subs` > 1 (backward only): a unit with more sampling points than the instantiation has slots is processed as
 // `subs` SUB-UNITS of `slots` points each -- the backward has no reduction across points, so the sub-units only share
-// the grad_out row.  The tiles of a (b,h) slice are ordered sub-unit-major (all queries of sub-unit 0, then sub-unit 1,
-// ...), which keeps the sub-unit -- hence the set of dead slots of a padded instantiation -- uniform across a warp.
+// the grad_out row.  A warp tile belongs to ONE sub-unit (so the dead slots of a padded instantiation are uniform
+// across the warp) and the sub-units of a query tile are consecutive tiles, i.e. they run on neighbouring warps of
+// the CTA at the same time: the row adds into the few, hot rows of the coarsest level (which all sit in the last
+// sub-unit) stay interleaved with the rest of the traffic.  (Sub-unit-major order, all queries of sub-unit 0 first,
+// measured 0.81 ms against 0.75 ms for the generic kernel on a 5-level pyramid: same-address serialisation in L2.)
 __device__ __forceinline__ TileUnit decode_tile(int tile, int tiles_per_bh, int g, int G, const KernelArgs &a,
                                                 int subs = 1, int slots = 0) {
     const int bh = tile / tiles_per_bh;
     int qt = tile - bh * tiles_per_bh;
     int sub = 0;
     if (subs > 1) {
-        const int tiles_per_sub = tiles_per_bh / subs;
-        sub = qt / tiles_per_sub;
-        qt -= sub * tiles_per_sub;
+        const int qt_full = qt;
+        qt = qt_full / subs;
+        sub = qt_full - qt * subs;
     }
     const int b = bh / a.H;
     const int h = bh - b * a.H;
