@@ -142,20 +142,27 @@ def b200_multiscale_deformable_attention(
     align_corners: bool,
 ) -> torch.Tensor:
     """CUDA route: validation (same two ``ValueError`` classes as frontend.py:84-95) then the autograd Function."""
-    for name, tensor in (("img", img), ("sampling_points", sampling_points), ("attention_weights", attention_weights)):
-        if tensor.dtype not in CUDA_DTYPES:
-            raise ValueError(f"Dtype of `{name}` should be in {list(CUDA_DTYPES)}, but got {tensor.dtype}.")
-    devices = [t.device for t in (img, img_shapes, sampling_points, attention_weights)]
-    if any(d.type != "cuda" for d in devices):
-        raise ValueError(f"Expected all inputs to be on gpu, but got {devices}.")
-    if len({d.index for d in devices}) != 1:
-        raise ValueError(f"Expected all inputs to be on the same gpu, but got {devices}.")
+    dtype, device = img.dtype, img.device
+    uniform = (dtype in CUDA_DTYPES and sampling_points.dtype == dtype and attention_weights.dtype == dtype
+               and device.type == "cuda" and img_shapes.device == device and sampling_points.device == device
+               and attention_weights.device == device)
+    if not uniform:   # slow path: find out what to complain about, or promote mixed dtypes
+        for name, tensor in (("img", img), ("sampling_points", sampling_points),
+                             ("attention_weights", attention_weights)):
+            if tensor.dtype not in CUDA_DTYPES:
+                raise ValueError(f"Dtype of `{name}` should be in {list(CUDA_DTYPES)}, but got {tensor.dtype}.")
+        devices = [t.device for t in (img, img_shapes, sampling_points, attention_weights)]
+        if any(d.type != "cuda" for d in devices):
+            raise ValueError(f"Expected all inputs to be on gpu, but got {devices}.")
+        if len({d.index for d in devices}) != 1:
+            raise ValueError(f"Expected all inputs to be on the same gpu, but got {devices}.")
+        if not torch.is_autocast_enabled("cuda"):
+            # the kernels take one storage dtype; mixed inputs are promoted (under autocast custom_fwd casts to fp32)
+            common = torch.promote_types(torch.promote_types(img.dtype, sampling_points.dtype),
+                                         attention_weights.dtype)
+            img, sampling_points, attention_weights = (t.to(common) for t in (img, sampling_points, attention_weights))
     if padding_mode not in ("border", "zeros"):
         raise ValueError(f"`padding_mode` should be 'border' or 'zeros', but got {padding_mode!r}.")
-    if not torch.is_autocast_enabled("cuda"):
-        # the kernels take one storage dtype; mixed inputs are promoted (under autocast custom_fwd casts to fp32)
-        common = torch.promote_types(torch.promote_types(img.dtype, sampling_points.dtype), attention_weights.dtype)
-        img, sampling_points, attention_weights = (t.to(common) for t in (img, sampling_points, attention_weights))
     if torch.compiler.is_compiling():
         # traced programs use the torch.library custom op (fake kernels + autograd formula, no graph break)
         from .ops import multiscale_deformable_attention_op

@@ -31,6 +31,7 @@ _DTYPE_CODE = {
 _PAD_CODE = {"zeros": _lib.PAD_ZEROS, "border": _lib.PAD_BORDER}
 
 _deterministic = False
+_VALIDATE = False   # set True to force the (synchronising) pyramid-size check without the environment variable
 
 
 def set_deterministic(enabled: bool) -> None:
@@ -83,12 +84,41 @@ def _shapes_i64(img_shapes: torch.Tensor) -> torch.Tensor:
     return img_shapes.contiguous()
 
 
-def _stream_ptr() -> ctypes.c_void_p:
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+class _on_device_of:
+    """Makes the tensor's device current for the launch (no-op, and cheap, when it already is) and hands out the raw
+    handle of torch's current stream on that device.  Per-call host cost matters for decoder-sized problems, where a
+    forward kernel takes ~10 us: torch.cuda.current_stream() / torch.cuda.device_of() cost more than that."""
+    __slots__ = ("index", "prev")
+
+    def __init__(self, t: torch.Tensor):
+        self.index = t.device.index
+        self.prev = -1
+
+    def __enter__(self):
+        if not _RAW_STREAM_API:   # public API (slower): torch builds without the private accessors
+            cur = torch.cuda.current_device()
+            if cur != self.index:
+                self.prev = cur
+                torch.cuda.set_device(self.index)
+            return torch.cuda.current_stream(self.index).cuda_stream
+        cur = torch._C._cuda_getDevice()
+        if cur != self.index:
+            self.prev = cur
+            torch._C._cuda_setDevice(self.index)
+        return torch._C._cuda_getCurrentRawStream(self.index)
+
+    def __exit__(self, *exc):
+        if self.prev >= 0:
+            torch.cuda.set_device(self.prev)
+        return False
 
 
-def _ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
-    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+_RAW_STREAM_API = all(hasattr(torch._C, n) for n in ("_cuda_getDevice", "_cuda_setDevice", "_cuda_getCurrentRawStream"))
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    """Device address for a `void *` parameter (ctypes turns None into NULL)."""
+    return None if t is None else t.data_ptr()
 
 
 def b200_multi_scale_deformable_attention_fwd(
@@ -110,10 +140,11 @@ def b200_multi_scale_deformable_attention_fwd(
         out = torch.empty((prob.B, prob.Q, prob.H, prob.D), dtype=img.dtype, device=img.device)
     else:
         _check_buffer(out, (prob.B, prob.Q, prob.H, prob.D), img, "out")
-    with torch.cuda.device_of(img):
+    with _on_device_of(img) as stream:
         rc = _lib.get_lib().msda_forward(_ptr(out), _ptr(img), _ptr(shapes), _ptr(pts), _ptr(aw), ctypes.byref(prob),
-                                   _stream_ptr())
-    _lib.check(rc, "msda_forward")
+                                         stream)
+    if rc:
+        _lib.check(rc, "msda_forward")
     return out
 
 
@@ -134,7 +165,7 @@ def b200_multi_scale_deformable_attention_bwd(
     img, pts, aw = _dense(img), _dense(sampling_points), _dense(attention_weights)
     shapes = _shapes_i64(img_shapes)
     prob = _problem(img, shapes, pts, aw, padding_mode, align_corners)
-    gout = _dense(out_grad.to(img.dtype))
+    gout = _dense(out_grad if out_grad.dtype == img.dtype else out_grad.to(img.dtype))
     if tuple(gout.shape) != (prob.B, prob.Q, prob.H, prob.D):
         raise ValueError(f"out_grad has shape {tuple(gout.shape)}, expected {(prob.B, prob.Q, prob.H, prob.D)}.")
     need_img, need_pts, need_aw = (bool(n) for n in needs)
@@ -156,12 +187,14 @@ def b200_multi_scale_deformable_attention_bwd(
     gimg = buffer(need_img, pre[0], img, "img_grad")
     gpts = buffer(need_pts, pre[1], pts, "sampling_points_grad")
     gaw = buffer(need_aw, pre[2], aw, "attention_weights_grad")
-    with torch.cuda.device_of(img):
-        ws_bytes = int(_lib.get_lib().msda_backward_workspace_bytes(ctypes.byref(prob), flags))
+    lib = _lib.get_lib()
+    with _on_device_of(img) as stream:
+        ws_bytes = int(lib.msda_backward_workspace_bytes(ctypes.byref(prob), flags))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=img.device) if ws_bytes else None
-        rc = _lib.get_lib().msda_backward(_ptr(gimg), _ptr(gpts), _ptr(gaw), _ptr(gout), _ptr(img), _ptr(shapes), _ptr(pts),
-                                    _ptr(aw), ctypes.byref(prob), flags, _ptr(ws), ws_bytes, _stream_ptr())
-    _lib.check(rc, "msda_backward")
+        rc = lib.msda_backward(_ptr(gimg), _ptr(gpts), _ptr(gaw), _ptr(gout), _ptr(img), _ptr(shapes), _ptr(pts),
+                               _ptr(aw), ctypes.byref(prob), flags, _ptr(ws), ws_bytes, stream)
+    if rc:
+        _lib.check(rc, "msda_backward")
     return gimg, gpts, gaw
 
 
@@ -203,10 +236,11 @@ def b200_module_core_fwd(value, img_shapes, proj, ref, padding_mode, align_corne
     prob = _module_problem(value, shapes, proj, ref, padding_mode, align_corners)
     _maybe_validate_shapes(shapes, prob.Npix)
     out = torch.empty((prob.B, prob.Q, prob.H, prob.D), dtype=value.dtype, device=value.device)
-    with torch.cuda.device_of(value):
+    with _on_device_of(value) as stream:
         rc = _lib.get_lib().msda_module_forward(_ptr(out), _ptr(value), _ptr(shapes), _ptr(proj), _ptr(ref),
-                                                int(ref.shape[-1]), ctypes.byref(prob), _stream_ptr())
-    _lib.check(rc, "msda_module_forward")
+                                                int(ref.shape[-1]), ctypes.byref(prob), stream)
+    if rc:
+        _lib.check(rc, "msda_module_forward")
     return out
 
 
@@ -216,21 +250,23 @@ def b200_module_core_bwd(out_grad, value, img_shapes, proj, ref, padding_mode, a
     value, proj, ref = _dense(value), _dense(proj), _dense(ref)
     shapes = _shapes_i64(img_shapes)
     prob = _module_problem(value, shapes, proj, ref, padding_mode, align_corners)
-    gout = _dense(out_grad.to(value.dtype))
+    gout = _dense(out_grad if out_grad.dtype == value.dtype else out_grad.to(value.dtype))
     need_value, need_proj, need_ref = (bool(n) for n in needs)
     flags = (_lib.BWD_NEED_IMG * need_value) | ((_lib.BWD_NEED_POINTS | _lib.BWD_NEED_WEIGHTS) * need_proj) \
         | (_lib.BWD_NEED_REF * need_ref)
     gvalue = torch.empty(value.shape, dtype=value.dtype, device=value.device) if need_value else None
     gproj = torch.empty(proj.shape, dtype=proj.dtype, device=value.device) if need_proj else None
     gref32 = torch.empty(ref.shape, dtype=torch.float32, device=value.device) if need_ref else None
-    with torch.cuda.device_of(value):
-        ws_bytes = int(_lib.get_lib().msda_backward_workspace_bytes(ctypes.byref(prob), flags & 7))
+    lib = _lib.get_lib()
+    with _on_device_of(value) as stream:
+        ws_bytes = int(lib.msda_backward_workspace_bytes(ctypes.byref(prob), flags & 7))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=value.device) if ws_bytes else None
-        rc = _lib.get_lib().msda_module_backward(
+        rc = lib.msda_module_backward(
             _ptr(gvalue), _ptr(gproj), _ptr(gref32), _ptr(gout), _ptr(value), _ptr(shapes), _ptr(proj), _ptr(ref),
-            int(ref.shape[-1]), ctypes.byref(prob), flags, _ptr(ws), ws_bytes, _stream_ptr())
-    _lib.check(rc, "msda_module_backward")
-    gref = gref32.to(ref.dtype) if need_ref else None
+            int(ref.shape[-1]), ctypes.byref(prob), flags, _ptr(ws), ws_bytes, stream)
+    if rc:
+        _lib.check(rc, "msda_module_backward")
+    gref = (gref32 if ref.dtype == torch.float32 else gref32.to(ref.dtype)) if need_ref else None
     return gvalue, gproj, gref
 
 
@@ -239,8 +275,8 @@ def level_table(img_shapes: torch.Tensor, num_pixels: int) -> torch.Tensor:
     shapes = _shapes_i64(img_shapes)
     L = shapes.shape[0]
     table = torch.empty((L + 1, 4), dtype=torch.int32, device=shapes.device)
-    with torch.cuda.device_of(shapes):
-        rc = _lib.get_lib().msda_level_table(_ptr(table), _ptr(shapes), L, int(num_pixels), _stream_ptr())
+    with _on_device_of(shapes) as stream:
+        rc = _lib.get_lib().msda_level_table(_ptr(table), _ptr(shapes), L, int(num_pixels), stream)
     _lib.check(rc, "msda_level_table")
     return table
 
@@ -249,6 +285,8 @@ def _maybe_validate_shapes(shapes: torch.Tensor, num_pixels: int) -> None:
     """Like the reference (frontend.py:71-105), the hot path never checks that sum(h*w) equals the pyramid length --
     doing so needs a device->host sync.  MSDA_B200_VALIDATE=1 turns the check on (debugging aid): the level table is
     built on the device by the library and read back."""
+    if not _VALIDATE and "MSDA_B200_VALIDATE" not in os.environ:
+        return
     if os.environ.get("MSDA_B200_VALIDATE", "0") == "0":
         return
     table = level_table(shapes, num_pixels).cpu()
