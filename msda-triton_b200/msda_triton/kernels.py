@@ -229,6 +229,23 @@ def module_core_supported(value: torch.Tensor, proj: torch.Tensor, ref: torch.Te
     return bool(_lib.get_lib().msda_module_supported(ctypes.byref(prob), int(ref.shape[-1])))
 
 
+def module_core_supported_static(value: torch.Tensor, proj: torch.Tensor, ref: torch.Tensor) -> bool:
+    """The eligibility rule of :func:`module_core_supported` (``msda_module_supported`` in the library) restated on
+    shapes and dtypes only, for traced programs (torch.compile cannot call into ctypes); a CPU test keeps the two in
+    step."""
+    if value.device.type != "cuda" or value.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+        return False
+    if not (value.dtype == proj.dtype == ref.dtype) or value.dim() != 4 or proj.dim() != 6 or ref.dim() != 3:
+        return False
+    batch, num_pixels, heads, channels = value.shape
+    queries, levels, points = proj.shape[1], proj.shape[3], proj.shape[4]
+    if not (channels in (32, 64) and levels * points == 16 and levels <= 8 and proj.shape[5] == 3
+            and ref.shape[2] in (2, 4)):
+        return False
+    # 32-bit offset arithmetic of the tuned kernels (tiled_offsets_fit in csrc/msda_tiled.cuh)
+    return num_pixels * heads * channels * value.element_size() < 2 ** 28 and batch * heads * queries < 2 ** 31
+
+
 def b200_module_core_fwd(value, img_shapes, proj, ref, padding_mode, align_corners) -> torch.Tensor:
     """out = MSDA(value, softmax / sampling-point arithmetic of (proj, ref)) without materialising the operands."""
     value, proj, ref = _dense(value), _dense(proj), _dense(ref)

@@ -5,6 +5,10 @@ an autograd formula, so a model that calls :func:`multiscale_deformable_attentio
 ``torch.compile(fullgraph=True)`` / ``torch.export`` without graph breaks and without running the CUDA code at trace
 time.  The eager public API (``msda_triton.multiscale_deformable_attention``) keeps using the
 ``torch.autograd.Function`` whose AMP contract mirrors the reference; under ``torch.compile`` it routes here.
+
+``torch.ops.msda_b200.module_forward`` / ``module_backward`` do the same for the fused module core
+(softmax + sampling-point arithmetic + operator in one kernel), so a compiled ``MultiscaleDeformableAttention`` keeps
+the fused fast path.
 """
 from __future__ import annotations
 
@@ -14,7 +18,7 @@ import torch
 
 from . import kernels
 
-__all__ = ["multiscale_deformable_attention_op"]
+__all__ = ["multiscale_deformable_attention_op", "module_core_op"]
 
 
 @torch.library.custom_op("msda_b200::forward", mutates_args=(), device_types="cuda")
@@ -74,3 +78,62 @@ def multiscale_deformable_attention_op(img, img_shapes, sampling_points, attenti
     expressed as a ``torch.library`` custom op (traceable by torch.compile / torch.export)."""
     return torch.ops.msda_b200.forward(img, img_shapes, sampling_points, attention_weights, padding_mode,
                                        bool(align_corners))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# fused module core
+# ---------------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("msda_b200::module_forward", mutates_args=(), device_types="cuda")
+def _module_forward(value: torch.Tensor, img_shapes: torch.Tensor, projection: torch.Tensor,
+                    reference_points: torch.Tensor, padding_mode: str, align_corners: bool) -> torch.Tensor:
+    return kernels.b200_module_core_fwd(value, img_shapes, projection, reference_points, padding_mode, align_corners)
+
+
+@_module_forward.register_fake
+def _(value, img_shapes, projection, reference_points, padding_mode, align_corners):
+    B, _, H, D = value.shape
+    return value.new_empty((B, projection.shape[1], H, D))
+
+
+@torch.library.custom_op("msda_b200::module_backward", mutates_args=(), device_types="cuda")
+def _module_backward(out_grad: torch.Tensor, value: torch.Tensor, img_shapes: torch.Tensor, projection: torch.Tensor,
+                     reference_points: torch.Tensor, padding_mode: str, align_corners: bool,
+                     needs: List[bool]) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    gv, gp, gr = kernels.b200_module_core_bwd(
+        out_grad, value, img_shapes, projection, reference_points, padding_mode, align_corners, needs=needs)
+    empty = value.new_empty((0,))
+    return (gv if gv is not None else empty, gp if gp is not None else empty, gr if gr is not None else empty)
+
+
+@_module_backward.register_fake
+def _(out_grad, value, img_shapes, projection, reference_points, padding_mode, align_corners, needs):
+    empty = value.new_empty((0,))
+    return (torch.empty_like(value, memory_format=torch.contiguous_format) if needs[0] else empty,
+            torch.empty_like(projection, memory_format=torch.contiguous_format) if needs[1] else empty,
+            torch.empty_like(reference_points, memory_format=torch.contiguous_format) if needs[2] else empty)
+
+
+def _module_setup_context(ctx, inputs, output):
+    value, img_shapes, projection, reference_points, padding_mode, align_corners = inputs
+    ctx.save_for_backward(value, img_shapes, projection, reference_points)
+    ctx.padding_mode = padding_mode
+    ctx.align_corners = align_corners
+
+
+def _module_autograd_backward(ctx, out_grad):
+    value, img_shapes, projection, reference_points = ctx.saved_tensors
+    needs = [bool(ctx.needs_input_grad[0]), bool(ctx.needs_input_grad[2]), bool(ctx.needs_input_grad[3])]
+    gv, gp, gr = torch.ops.msda_b200.module_backward(
+        out_grad.contiguous(), value, img_shapes, projection, reference_points, ctx.padding_mode, ctx.align_corners,
+        needs)
+    return (gv if needs[0] else None, None, gp if needs[1] else None, gr if needs[2] else None, None, None)
+
+
+_module_forward.register_autograd(_module_autograd_backward, setup_context=_module_setup_context)
+
+
+def module_core_op(value, img_shapes, projection, reference_points, padding_mode: str,
+                   align_corners: bool) -> torch.Tensor:
+    """``msda_triton.frontend.fused_module_core`` as a ``torch.library`` custom op (same operands, same result)."""
+    return torch.ops.msda_b200.module_forward(value, img_shapes, projection, reference_points, padding_mode,
+                                              bool(align_corners))

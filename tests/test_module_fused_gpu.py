@@ -167,3 +167,55 @@ def test_module_matches_reference_module_golden_cuda(name, dtype, fused):
             check_module_against_golden(g, module, inputs, shapes, rtol=2e-4, atol_scale=2e-5, max_outliers=2)
     finally:
         os.environ.pop("MSDA_B200_FUSED_MODULE")
+
+
+@pytest.mark.parametrize("coords", [2, 4])
+def test_compiled_module_keeps_the_fused_core(coords):
+    """torch.compile(fullgraph=True) of the nn.Module: the fused core runs behind torch.ops.msda_b200.module_forward /
+    module_backward (no graph break, no composed fallback) and reproduces the eager fused path."""
+    import copy
+    from msda_triton import MultiscaleDeformableAttention
+    torch.manual_seed(11)
+    emb, heads, levels, points = 256, 8, 4, 4
+    npix = sum(h * w for h, w in BENCH_PYRAMID)
+    img = torch.randn(2, npix, emb, device="cuda")
+    queries = torch.randn(2, 150, emb, device="cuda")
+    ref_pts = torch.rand(2, 150, coords, device="cuda") * 0.8 + 0.1
+    shapes = torch.tensor(BENCH_PYRAMID, device="cuda")
+    module = MultiscaleDeformableAttention(emb, emb, levels, heads, points, "zeros", False).cuda()
+    twin = copy.deepcopy(module)
+
+    def run(mod, fn):
+        i, q, r = (t.clone().requires_grad_(True) for t in (img, queries, ref_pts))
+        out = fn(i, shapes, q, r)
+        out.square().sum().backward()
+        return [out.detach(), i.grad, q.grad, r.grad] + [p.grad for p in mod.parameters()]
+
+    want = run(module, module)
+    calls = {"fwd": 0}
+    from msda_triton import kernels
+    real = kernels.b200_module_core_fwd
+
+    def counting(*args, **kwargs):
+        calls["fwd"] += 1
+        return real(*args, **kwargs)
+
+    kernels.b200_module_core_fwd = counting
+    try:
+        got = run(twin, torch.compile(twin, backend="aot_eager", fullgraph=True))
+    finally:
+        kernels.b200_module_core_fwd = real
+    assert calls["fwd"] == 1                      # the compiled program went through the fused custom op
+    for a, b in zip(got, want):
+        b = to_np(b)
+        assert_close(to_np(a), b, 2e-4, 2e-5 * max(1e-3, np.abs(b).max()), "compiled vs eager", max_outliers=8)
+
+
+def test_module_core_custom_op_opcheck():
+    value = torch.randn(1, 85, 8, 32, device="cuda", requires_grad=True)
+    proj = torch.randn(1, 40, 8, 4, 4, 3, device="cuda", requires_grad=True)
+    ref = torch.rand(1, 40, 2, device="cuda", requires_grad=True)
+    shapes = torch.tensor([(8, 8), (4, 4), (2, 2), (1, 1)], device="cuda")
+    import msda_triton.ops  # noqa: F401  (registers the ops)
+    torch.library.opcheck(torch.ops.msda_b200.module_forward.default, (value, shapes, proj, ref, "border", True),
+                          test_utils=("test_schema", "test_faketensor", "test_autograd_registration"))
