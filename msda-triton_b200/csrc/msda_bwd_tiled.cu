@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     wave_range(ws, wave, blockIdx.x, gridDim.x, t_begin, t_end);
 
     int tile = t_begin + warp;
-    if (tile >= t_end) continue;
+    if (tile < t_end) {
 
     TileUnit tu = decode_tile(tile, tiles_per_bh, g, G, a, subs, LK);
     LaneOperands<T, PPL, FUSED> op;
@@ -301,6 +301,8 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll
         for (int i = 0; i < VEC; ++i) go[i] = go_n[i];
     }
+    }
+    wave_pace_cta(ws, wave);
     }  // waves
 }
 
@@ -318,7 +320,11 @@ static cudaError_t launch_tiled_t(const KernelArgs &a, int sm_count, cudaStream_
     const int grid = (int)(want < sm_count ? (want < 1 ? 1 : want) : sm_count);
     // one wave keeps its pyramid slices AND (when grad_img is produced) the fp32 grad_img slices in L2
     const size_t per_slice_factor = (a.flags & kNeedImg) ? sizeof(T) + sizeof(float) : sizeof(T);
-    const WaveSchedule ws = make_wave_schedule(a, tiles_per_bh, per_slice_factor, kBwdL2Budget);
+    WaveSchedule ws = make_wave_schedule(a, tiles_per_bh, per_slice_factor, kBwdL2Budget);
+    if (ws.waves > 1 && grid == sm_count) {   // many waves: keep the persistent CTAs on the same wave (wave_pace)
+        const cudaError_t e = acquire_pace_counter(st, &ws.pace);
+        if (e != cudaSuccess) return e;
+    }
     if (a.border)
         msda_bwd_tiled_kernel<T, LANES, LK, true, NB, THREADS, FUSED, VEC, PADDED, SPLIT>
             <<<grid, THREADS, 0, st>>>(a, ws, subs);
@@ -403,7 +409,10 @@ cudaError_t launch_backward_tiled(const KernelArgs &a, int dtype, int sm_count, 
     // grad_img ONLY (points / weights do not require grad): no pyramid gathers are needed at all, and the scatter-only
     // kernel with in-CTA binning is the faster way to produce it (bench shape: 0.29 ms versus 0.45 ms) -- provided there
     // are enough 384-query super-tiles to fill the machine.
-    if (a.flags == kNeedImg && dtype == 0 && a.D == 32 &&
+    // The scatter kernel has no L2-sized waves, so it only takes batches whose pyramid + grad_img fit one wave (B=64
+    // encoder shape: 21.1 ms, worse than the full tuned backward).
+    const bool one_wave = (unsigned long long)a.B * a.Npix * a.H * a.D * (sizeof(float) + sizeof(float)) <= kBwdL2Budget;
+    if (a.flags == kNeedImg && dtype == 0 && a.D == 32 && one_wave &&
         (long long)a.B * a.H * ((a.Q + 383) / 384) >= 2LL * sm_count) {
         const cudaError_t e = launch_backward_scatter(a, dtype, sm_count, st);
         if (e != cudaErrorNotSupported) return e;

@@ -26,6 +26,8 @@ __global__ void __launch_bounds__(THREADS, 1)
     static_assert(LANES % NB == 0, "batch must divide the group");
 
     __shared__ Level s_lv[8];   // tuned kernels take L <= 8
+    __shared__ unsigned s_pace[kPaceRing];
+    if (threadIdx.x < kPaceRing) s_pace[threadIdx.x] = 0;
     build_level_table(s_lv, a.shapes, a.L);
 
     const T *__restrict__ img = static_cast<const T *>(a.img);
@@ -42,7 +44,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     wave_range(ws, wave, blockIdx.x, gridDim.x, t_begin, t_end);
 
     int tile = t_begin + warp;
-    if (tile >= t_end) continue;
+    if (tile < t_end) {
 
     // software pipeline: sampling points / weights of the next warp tile are in flight while this one is processed
     TileUnit tu = decode_tile(tile, tiles_per_bh, g, G, a);
@@ -120,6 +122,8 @@ __global__ void __launch_bounds__(THREADS, 1)
         tu = tu_n;
         op = op_n;
     }
+    }
+    wave_pace_warp(ws, wave, s_pace, lane, nwarps);
     }  // waves
 }
 
@@ -132,7 +136,11 @@ static cudaError_t launch_tiled_cfg(const KernelArgs &a, int sm_count, cudaStrea
     const int warps = THREADS / 32;
     const int want = (total_tiles + warps - 1) / warps;
     const int grid = (int)(want < sm_count ? (want < 1 ? 1 : want) : sm_count);
-    const WaveSchedule ws = make_wave_schedule(a, tiles_per_bh, sizeof(T), kFwdL2Budget);
+    WaveSchedule ws = make_wave_schedule(a, tiles_per_bh, sizeof(T), kFwdL2Budget);
+    if (ws.waves > 1 && grid == sm_count) {   // many waves: keep the persistent CTAs on the same wave (wave_pace)
+        const cudaError_t e = acquire_pace_counter(st, &ws.pace);
+        if (e != cudaSuccess) return e;
+    }
     if (a.border)
         msda_fwd_tiled_kernel<T, LANES, LK, true, NB, THREADS, FUSED, PADDED><<<grid, THREADS, 0, st>>>(a, ws);
     else

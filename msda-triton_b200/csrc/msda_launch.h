@@ -33,4 +33,7 @@ cudaError_t launch_backward_det(const KernelArgs &a, int dtype, int vec, void *w
 cudaError_t launch_round_grad_img(void *dst, const float *src, long long n, int dtype, int D, int permuted_lanes,
                                   cudaStream_t st);
 
+// Arrival counter for wave pacing (msda_pace.cu): *slot = a device word zeroed on `st`, or nullptr when pacing is off.
+cudaError_t acquire_pace_counter(cudaStream_t st, unsigned **slot);
+
 }  // namespace msda

@@ -20,8 +20,11 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default=bench.HEADLINE)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--points", default="unit", choices=["unit", "local"])
+ap.add_argument("--batch", type=int, default=0, help="override the workload's batch size")
 ns = ap.parse_args()
 
+if ns.batch:
+    bench.WORKLOADS[ns.workload] = (ns.batch,) + tuple(bench.WORKLOADS[ns.workload][1:])
 B, Q, H, D, pyr, Kp, pm, ac = bench.WORKLOADS[ns.workload]
 t, shapes = bench.make_inputs(ns.workload, seed=0, device="cuda")
 for _ in range(ns.steps):
