@@ -409,10 +409,10 @@ cudaError_t launch_backward_tiled(const KernelArgs &a, int dtype, int sm_count, 
     // grad_img ONLY (points / weights do not require grad): no pyramid gathers are needed at all, and the scatter-only
     // kernel with in-CTA binning is the faster way to produce it (bench shape: 0.29 ms versus 0.45 ms) -- provided there
     // are enough 384-query super-tiles to fill the machine.
-    // The scatter kernel has no L2-sized waves, so it only takes batches whose pyramid + grad_img fit one wave (B=64
-    // encoder shape: 21.1 ms, worse than the full tuned backward).
-    const bool one_wave = (unsigned long long)a.B * a.Npix * a.H * a.D * (sizeof(float) + sizeof(float)) <= kBwdL2Budget;
-    if (a.flags == kNeedImg && dtype == 0 && a.D == 32 && one_wave &&
+    // The scatter kernel has no L2-sized waves, so it only takes batches whose pyramid + grad_img stay L2-resident
+    // as a whole (DETR encoder B=2: 91 MB, 0.39 ms versus 0.51 ms; B=64: 21.1 ms, worse than the full tuned backward).
+    const bool l2_resident = (unsigned long long)a.B * a.Npix * a.H * a.D * (2 * sizeof(float)) <= (96ull << 20);
+    if (a.flags == kNeedImg && dtype == 0 && a.D == 32 && l2_resident &&
         (long long)a.B * a.H * ((a.Q + 383) / 384) >= 2LL * sm_count) {
         const cudaError_t e = launch_backward_scatter(a, dtype, sm_count, st);
         if (e != cudaErrorNotSupported) return e;
