@@ -373,3 +373,22 @@ def test_addressing_beyond_2_to_31_elements(K, Kp):
         torch.testing.assert_close(gi[sl], gi1, rtol=1e-5, atol=1e-6)     # atomics: order may differ
     del img, gi
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("slack", ["0", "1"])
+def test_wave_pacing_many_waves(K, slack):
+    """Multi-wave schedule with the wave pacing active (one (b,h) slice per wave -> 16 waves on a full persistent grid):
+    same forward bits and the same gradients as the single-wave schedule."""
+    img, s, pts, aw, go = make_inputs(2, 3000, 8, 32, BENCH_PYRAMID, 4, seed=13, points="wide")
+    base = run_cuda(K, img, s, pts, aw, go, "zeros", False)
+    os.environ["MSDA_B200_SLICES_PER_WAVE"] = "1"
+    os.environ["MSDA_B200_PACE_SLACK"] = slack
+    try:
+        paced = run_cuda(K, img, s, pts, aw, go, "zeros", False)
+    finally:
+        os.environ.pop("MSDA_B200_SLICES_PER_WAVE")
+        os.environ.pop("MSDA_B200_PACE_SLACK")
+    assert torch.equal(paced[0], base[0])
+    assert torch.equal(paced[2], base[2]) and torch.equal(paced[3], base[3])
+    b = to_np(base[1])
+    assert_close(to_np(paced[1]), b, 1e-5, 2e-6 * np.abs(b).max(), "grad_img")
