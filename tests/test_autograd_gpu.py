@@ -129,6 +129,27 @@ def test_cuda_graph_capture():
         assert torch.equal(a, b)
 
 
+def test_cuda_graph_capture_of_a_paced_multi_wave_launch(monkeypatch):
+    """Multi-wave launches zero an arrival counter on the stream (memset node) and pace their CTAs on it: the pair
+    captures into a CUDA graph and replays (the graph reuses its counter slot)."""
+    from msda_triton import kernels as K
+    monkeypatch.setenv("MSDA_B200_SLICES_PER_WAVE", "1")           # 16 waves on a full persistent grid
+    img, s, pts, aw, go = (t.cuda() for t in make_inputs(2, 3000, 8, 32, BENCH_PYRAMID, 4, seed=14))
+    eager_out = K.b200_multi_scale_deformable_attention_fwd(img, s, pts, aw, "zeros", False)
+    eager_g = K.b200_multi_scale_deformable_attention_bwd(go, img, s, pts, aw, "zeros", False)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = K.b200_multi_scale_deformable_attention_fwd(img, s, pts, aw, "zeros", False)
+        g = K.b200_multi_scale_deformable_attention_bwd(go, img, s, pts, aw, "zeros", False)
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, eager_out)
+    assert torch.equal(g[1], eager_g[1]) and torch.equal(g[2], eager_g[2])
+    torch.testing.assert_close(g[0], eager_g[0], rtol=1e-4, atol=1e-4)
+
+
 def test_host_pipeline_matches_device_path():
     """msda_triton.host.HostMsda (pinned host buffers, chunked H2D / kernels / D2H overlap) == plain device calls."""
     from msda_triton import kernels as K
