@@ -70,3 +70,38 @@ def test_random_problem_16bit_storage(seed):
         assert t.dtype == dtype
         assert_close(to_np(t), r, eps, eps * 2e-2 * max(1e-30, np.abs(r).max()), f"{what} {n}",
                      max_outliers=int(budget * r.size) + (2 if budget else 0))
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_many_points(seed):
+    """Head widths the tuned kernels cover (D = 32 / 64) with 17 ... 128 sampling points per unit: sub-unit backward
+    (exact and ragged slot counts), padded / generic forward."""
+    from msda_triton import kernels as K_
+    from oracle import msda_oracle
+    rng = np.random.default_rng(9000 + seed)
+    while True:
+        L, K = int(rng.integers(1, 9)), int(rng.integers(1, 17))
+        if 16 < L * K <= 128:
+            break
+    D = 32 if seed % 3 else 64
+    H, B, Q = int(rng.integers(1, 9)), int(rng.integers(1, 3)), int(rng.integers(1, 120))
+    shapes = sorted(((int(rng.integers(1, 20)), int(rng.integers(1, 20))) for _ in range(L)), key=lambda s: -s[0] * s[1])
+    pm, ac = str(rng.choice(["zeros", "border"])), bool(rng.integers(0, 2))
+    dtype = torch.float32 if seed % 4 else torch.bfloat16
+    img, s, pts, aw, go = make_inputs(B, Q, H, D, shapes, K, dtype=dtype, seed=seed, points="wide", weights="softmax_lk")
+    dev = [t.cuda() for t in (img, s, pts, aw, go)]
+    out = K_.b200_multi_scale_deformable_attention_fwd(dev[0], dev[1], dev[2], dev[3], pm, ac)
+    gi, gp, ga = K_.b200_multi_scale_deformable_attention_bwd(dev[4], dev[0], dev[1], dev[2], dev[3], pm, ac)
+    ref_out = msda_oracle.forward(img, s, pts, aw, pm, ac)
+    rgi, rgp, rga = msda_oracle.backward(go, img, s, pts, aw, pm, ac)
+    what = f"seed {seed}: B={B} Q={Q} H={H} D={D} shapes={shapes} K={K} {pm}/{ac} {dtype}"
+    if dtype == torch.float32:
+        assert_close(to_np(out), ref_out, 1e-5, 2e-6 * max(1.0, np.abs(ref_out).max()), what + " out")
+        for t, r, n in ((gi, rgi, "grad_img"), (gp, rgp, "grad_points"), (ga, rga, "grad_weights")):
+            assert_close(to_np(t), r, 1e-4, 1e-5 * max(1e-30, np.abs(r).max()), f"{what} {n}")
+    else:
+        eps = 2.0 ** -7
+        for t, r, n, budget in ((out, ref_out, "out", 0.0), (gi, rgi, "grad_img", 0.0), (ga, rga, "grad_weights", 0.0),
+                                (gp, rgp, "grad_points", 0.02)):
+            assert_close(to_np(t), r, eps, eps * 2e-2 * max(1e-30, np.abs(r).max()), f"{what} {n}",
+                         max_outliers=int(budget * r.size) + (2 if budget else 0))
