@@ -16,7 +16,7 @@ cudaError_t launch_forward_tiled(const KernelArgs &a, int dtype, int sm_count, c
 cudaError_t launch_backward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st);
 
 // Fused module core (raw projection + reference points in, see msda_tiled.cuh).  cudaErrorNotSupported when the
-// problem is outside (fp32|fp16|bf16) x D=32 x L*K=16.
+// problem is outside (fp32|fp16|bf16) x D in {32, 64} x L*K=16.
 cudaError_t launch_module_forward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st);
 cudaError_t launch_module_backward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st);
 
