@@ -392,3 +392,24 @@ def test_wave_pacing_many_waves(K, slack):
     assert torch.equal(paced[2], base[2]) and torch.equal(paced[3], base[3])
     b = to_np(base[1])
     assert_close(to_np(paced[1]), b, 1e-5, 2e-6 * np.abs(b).max(), "grad_img")
+
+
+@pytest.mark.parametrize("Kp", [4, 3], ids=["tuned", "generic"])
+@pytest.mark.parametrize("pm", ["zeros", "border"])
+def test_nonfinite_points_are_memory_safe(K, Kp, pm):
+    """NaN / +-Inf / 1e30 sampling points (a diverged training step) must not fault or touch other units: indices are
+    clamped in floating point before the integer cast (kernels.py:166-169), so only the poisoned queries change."""
+    img, s, pts, aw, go = make_inputs(2, 257, 8, 32, BENCH_PYRAMID, Kp, seed=21, points="wide")
+    clean = run_cuda(K, img, s, pts, aw, go, pm, False)
+    bad = pts.clone()
+    poison = [float("nan"), float("inf"), -float("inf"), 1e30, -1e30]
+    for i, v in enumerate(poison):
+        bad[0, 10 + i, :, :, :, i % 2] = v        # queries 10..14 of image 0
+    out, gi, gp, ga = run_cuda(K, img, s, bad, aw, go, pm, False)
+    keep = torch.ones(257, dtype=torch.bool)
+    keep[10:15] = False
+    assert torch.equal(out[1], clean[0][1]) and torch.equal(out[0, keep.cuda()], clean[0][0, keep.cuda()])
+    assert torch.equal(gp[0, keep.cuda()], clean[2][0, keep.cuda()])
+    assert torch.equal(ga[0, keep.cuda()], clean[3][0, keep.cuda()])
+    b = to_np(clean[1][1])
+    assert_close(to_np(gi[1]), b, 1e-5, 2e-6 * np.abs(b).max(), "grad_img of the clean image")
