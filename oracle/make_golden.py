@@ -121,9 +121,9 @@ def make_module_golden(f):
     """The reference nn.Module (frontend.py:175-292) with seeded weights on CPU: state_dict, inputs, output and the
     gradients of a scalar loss -- pins the module-level semantics (projection interleaving, softmax over L*K, the
     (h, w) normaliser of 2-d reference points, the 4-d reference-point formula)."""
-    for coords, pm, ac in ((2, "zeros", False), (4, "border", True)):
-        torch.manual_seed(100 + coords)
-        emb, hidden, levels, heads, points = 16, 64, 4, 2, 4          # head_dim 32, L*K = 16: the fused CUDA shape
+    for coords, pm, ac, hidden in ((2, "zeros", False, 64), (4, "border", True, 64), (2, "border", False, 128)):
+        torch.manual_seed(100 + coords + (0 if hidden == 64 else hidden))
+        emb, levels, heads, points = 16, 4, 2, 4     # head_dim 32 (hidden 64) / 64 (hidden 128), L*K = 16: fused CUDA shapes
         shapes = [(9, 12), (5, 6), (3, 3), (2, 2)]
         npix = sum(h * w for h, w in shapes)
         module = f.MultiscaleDeformableAttention(emb, hidden, levels, heads, points, pm, ac).double()
@@ -141,7 +141,7 @@ def make_module_golden(f):
                    img_shapes=np.array(shapes), out=out.detach().numpy(), grad_img=img.grad.numpy(),
                    grad_queries=queries.grad.numpy(), grad_reference_points=ref.grad.numpy(),
                    config=np.array([emb, hidden, levels, heads, points, coords, int(ac)]), padding_mode=np.array(pm))
-        path = OUT / f"module_ref{coords}d_float64.npz"
+        path = OUT / (f"module_ref{coords}d_float64.npz" if hidden == 64 else f"module_ref{coords}d_hd64_float64.npz")
         np.savez_compressed(path, **rec)
         print(f"wrote {path}  ({path.stat().st_size / 1024:.1f} KiB)")
 

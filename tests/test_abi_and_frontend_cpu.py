@@ -174,7 +174,7 @@ def test_grid_sample_port_matches_oracle():
     assert_close(to_np(ga), rga, 1e-9, 1e-10, "grad_weights")
 
 
-@pytest.mark.parametrize("name", ["module_ref2d_float64", "module_ref4d_float64"])
+@pytest.mark.parametrize("name", ["module_ref2d_float64", "module_ref4d_float64", "module_ref2d_hd64_float64"])
 def test_module_matches_reference_module_golden_cpu(name):
     """Our nn.Module, loaded with the REFERENCE module's state_dict, reproduces the reference module's output and all
     gradients (golden vectors from oracle/make_golden.py) on the CPU-tensor route."""

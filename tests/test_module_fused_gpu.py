@@ -150,7 +150,7 @@ def test_fused_core_rejects_unsupported_and_falls_back():
     assert out.shape == (1, 5, 64)
 
 
-@pytest.mark.parametrize("name", ["module_ref2d_float64", "module_ref4d_float64"])
+@pytest.mark.parametrize("name", ["module_ref2d_float64", "module_ref4d_float64", "module_ref2d_hd64_float64"])
 @pytest.mark.parametrize("dtype,fused", [(torch.float64, False), (torch.float32, True), (torch.float32, False)],
                          ids=["f64-composed", "f32-fused", "f32-composed"])
 def test_module_matches_reference_module_golden_cuda(name, dtype, fused):
