@@ -18,10 +18,11 @@ constexpr size_t kFwdL2Budget = 24u << 20;
 // points; softmax and the sampling-point arithmetic happen in registers, sampling_points / attention_weights are never
 // materialised.
 // PADDED = the unit has a.LK <= LK points; the LK - a.LK trailing slots are skipped (warp-uniformly) by every loop.
-template <typename T, int LANES, int LK, bool BORDER, int NB, int THREADS, bool FUSED, bool PADDED>
+template <typename T, int LANES, int LK, bool BORDER, int NB, int THREADS, bool FUSED, bool PADDED, int VECB = 16>
 __global__ void __launch_bounds__(THREADS, 1)
     msda_fwd_tiled_kernel(const KernelArgs a, const WaveSchedule ws) {
-    using Cfg = TiledCfg<T, LANES, LK>;
+    using Cfg = TiledCfg<T, LANES, LK, VECB>;
+    using Raw = typename RawSlice<VECB>::type;
     constexpr int VEC = Cfg::VEC, G = Cfg::G, PPL = Cfg::PPL;
     static_assert(LANES % NB == 0, "batch must divide the group");
 
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         for (int pp = 0; pp < PPL; ++pp) {
 #pragma unroll
             for (int jj0 = 0; jj0 < LANES; jj0 += NB) {
-                uint4 raw[NB][4];
+                Raw raw[NB][4];
                 float fx[NB], fy[NB], fw[NB];
                 unsigned msk[NB];
 #pragma unroll
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                     // (kernels.py:227-231: out-of-range corners read as 0) is applied when the values are consumed,
                     // which keeps the 4*NB loads independent and in flight together
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) raw[n][c] = gather_row(lane_base, o[c]);
+                    for (int c = 0; c < 4; ++c) raw[n][c] = gather_slice<VECB>(lane_base, o[c]);
                 }
 #pragma unroll
                 for (int n = 0; n < NB; ++n) {
@@ -127,9 +128,9 @@ __global__ void __launch_bounds__(THREADS, 1)
     }  // waves
 }
 
-template <typename T, int LANES, int LK, int THREADS, int NB, bool FUSED = false, bool PADDED = false>
+template <typename T, int LANES, int LK, int THREADS, int NB, bool FUSED = false, bool PADDED = false, int VECB = 16>
 static cudaError_t launch_tiled_cfg(const KernelArgs &a, int sm_count, cudaStream_t st) {
-    constexpr int G = TiledCfg<T, LANES, LK>::G;
+    constexpr int G = TiledCfg<T, LANES, LK, VECB>::G;
     if (!tiled_offsets_fit(a, sizeof(T))) return cudaErrorNotSupported;
     const int tiles_per_bh = (a.Q + G - 1) / G;
     const int total_tiles = a.B * a.H * tiles_per_bh;
@@ -142,9 +143,9 @@ static cudaError_t launch_tiled_cfg(const KernelArgs &a, int sm_count, cudaStrea
         if (e != cudaSuccess) return e;
     }
     if (a.border)
-        msda_fwd_tiled_kernel<T, LANES, LK, true, NB, THREADS, FUSED, PADDED><<<grid, THREADS, 0, st>>>(a, ws);
+        msda_fwd_tiled_kernel<T, LANES, LK, true, NB, THREADS, FUSED, PADDED, VECB><<<grid, THREADS, 0, st>>>(a, ws);
     else
-        msda_fwd_tiled_kernel<T, LANES, LK, false, NB, THREADS, FUSED, PADDED><<<grid, THREADS, 0, st>>>(a, ws);
+        msda_fwd_tiled_kernel<T, LANES, LK, false, NB, THREADS, FUSED, PADDED, VECB><<<grid, THREADS, 0, st>>>(a, ws);
     return cudaGetLastError();
 }
 
@@ -155,7 +156,7 @@ template <typename T, int LANES, int LK, bool PADDED = false>
 static cudaError_t launch_tiled_t(const KernelArgs &a, int sm_count, cudaStream_t st) {
     if constexpr (!PADDED) {
         if (const char *e = std::getenv("MSDA_B200_FWD_VARIANT")) {   // tuning knob
-            if (std::atoi(e) == 1) return launch_tiled_cfg<T, LANES, LK, 512, 4>(a, sm_count, st);
+            if (e[0] == '1') return launch_tiled_cfg<T, LANES, LK, 512, 4>(a, sm_count, st);
         }
     }
     // lanes that own >= 3 points keep more state: stay at 128 registers there
@@ -172,8 +173,18 @@ cudaError_t launch_forward_tiled(const KernelArgs &a, int dtype, int sm_count, c
     if (a.L > 8 || a.LK > 32) return cudaErrorNotSupported;
     if (a.LK == 16) {
         if (dtype == 0) {
-            if (a.D == 32) return launch_tiled_t<float, 8, 16>(a, sm_count, st);
-            if (a.D == 64) return launch_tiled_t<float, 16, 16>(a, sm_count, st);
+            // fp32 rows are gathered with 256-bit loads (LDG.E.256, sm_100): 4 lanes x 32 bytes per 128-byte row, so a
+            // warp iteration covers 8 units -- half the load, shuffle and address instructions per unit of the
+            // 8 lanes x 128-bit layout.  Measured (bench border / zeros / DETR encoder): 0.141 / 0.141 / 0.166 ms
+            // versus 0.148 / 0.154 / 0.172 ms (no gain for 256-byte fp32 rows or 128-byte 16-bit rows, which stay on
+            // 128-bit lanes).  MSDA_B200_FWD_VARIANT=0|1 select the 128-bit layouts (measurement).
+            const char *e = std::getenv("MSDA_B200_FWD_VARIANT");
+            const bool wide = !(e && (e[0] == '0' || e[0] == '1'));
+            if (a.D == 32) {
+                if (wide) return launch_tiled_cfg<float, 4, 16, 512, 2, false, false, 32>(a, sm_count, st);
+                return launch_tiled_t<float, 8, 16>(a, sm_count, st);
+            }
+            if (a.D == 64) return launch_tiled_t<float, 16, 16>(a, sm_count, st);   // 256-byte rows: no gain from wide lanes
         } else if (dtype == 1) {
             if (a.D == 32) return launch_tiled_t<__half, 4, 16>(a, sm_count, st);
             if (a.D == 64) return launch_tiled_t<__half, 8, 16>(a, sm_count, st);
@@ -210,7 +221,12 @@ cudaError_t launch_forward_tiled(const KernelArgs &a, int dtype, int sm_count, c
 cudaError_t launch_module_forward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st) {
     if (a.LK != 16 || a.L > 8 || (a.ref_dim != 2 && a.ref_dim != 4)) return cudaErrorNotSupported;
     if (a.D == 32) {
-        if (dtype == 0) return launch_tiled_cfg<float, 8, 16, 1024, 2, true>(a, sm_count, st);
+        if (dtype == 0) {
+            const char *e = std::getenv("MSDA_B200_FWD_VARIANT");
+            if (!(e && (e[0] == '0' || e[0] == '1')))
+                return launch_tiled_cfg<float, 4, 16, 512, 2, true, false, 32>(a, sm_count, st);
+            return launch_tiled_cfg<float, 8, 16, 1024, 2, true>(a, sm_count, st);
+        }
         if (dtype == 1) return launch_tiled_cfg<__half, 4, 16, 512, 4, true>(a, sm_count, st);
         if (dtype == 2) return launch_tiled_cfg<__nv_bfloat16, 4, 16, 512, 4, true>(a, sm_count, st);
     } else if (a.D == 64) {   // hidden 512 / 8 heads: the reference README's module example

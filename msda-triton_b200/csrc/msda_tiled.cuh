@@ -1,7 +1,8 @@
 // msda_tiled.cuh -- shared pieces of the tuned ("tiled") forward/backward kernels.
 //
 // The tuned kernels cover the shapes BASELINE.json names: L*K == 16 sampling points per unit and a pixel row of
-// 64..256 bytes per head (D=32 fp32 -> 128 B -> 8 lanes x 128-bit; D=32 bf16/fp16 -> 64 B -> 4 lanes).
+// 64..256 bytes per head (D=32 fp32 -> 128 B -> 8 lanes x 128-bit, or 4 lanes x 256-bit in the forward; D=32 bf16/fp16
+// -> 64 B -> 4 lanes).
 //
 // Scheduling: the grid is PERSISTENT, one CTA per SM.  Units are ordered (b, h, q) with q fastest and cut into
 // contiguous ranges, one range per CTA, so at any moment every warp of an SM gathers from the SAME (b,h) slice of
@@ -21,8 +22,8 @@
 
 namespace msda {
 
-template <typename T, int LANES, int LK> struct TiledCfg {
-    static constexpr int VEC = 16 / (int)sizeof(T);   // elements per 128-bit lane load
+template <typename T, int LANES, int LK, int VECB = 16> struct TiledCfg {
+    static constexpr int VEC = VECB / (int)sizeof(T);   // elements per lane load (128-bit; 256-bit with VECB = 32)
     static constexpr int G = 32 / LANES;              // units per warp iteration
     static constexpr int PPL = LK / LANES;            // sampling points resolved by each lane
     static_assert(LANES * PPL == LK, "LK must be a multiple of LANES");
@@ -335,11 +336,22 @@ __device__ __forceinline__ void derive_operands(const KernelArgs &a, const Level
 template <int BYTES> struct RawSlice;
 template <> struct RawSlice<16> { using type = uint4; };
 template <> struct RawSlice<8> { using type = uint2; };
+struct alignas(32) Raw256 { uint4 lo, hi; };
+template <> struct RawSlice<32> { using type = Raw256; };   // sm_100: LDG.E.256
 
 template <int BYTES>
 __device__ __forceinline__ typename RawSlice<BYTES>::type gather_slice(const unsigned char *__restrict__ lane_base,
                                                                        unsigned byte_off) {
     return __ldg(reinterpret_cast<const typename RawSlice<BYTES>::type *>(lane_base + byte_off));
+}
+
+template <>
+__device__ __forceinline__ Raw256 gather_slice<32>(const unsigned char *__restrict__ lane_base, unsigned byte_off) {
+    Raw256 r;
+    asm("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(r.lo.x), "=r"(r.lo.y), "=r"(r.lo.z), "=r"(r.lo.w), "=r"(r.hi.x), "=r"(r.hi.y), "=r"(r.hi.z), "=r"(r.hi.w)
+        : "l"(lane_base + byte_off));
+    return r;
 }
 
 __device__ __forceinline__ uint4 gather_row(const unsigned char *__restrict__ lane_base, unsigned byte_off) {
@@ -369,6 +381,18 @@ template <typename T, int VEC> __device__ __forceinline__ void widen_row(const u
         widen_word<T>(raw.y, v[2], v[3]);
         widen_word<T>(raw.z, v[4], v[5]);
         widen_word<T>(raw.w, v[6], v[7]);
+    }
+}
+template <typename T, int VEC> __device__ __forceinline__ void widen_row(const Raw256 raw, float (&v)[VEC]) {
+    static_assert(VEC * sizeof(T) == 32, "32-byte slices: eight fp32 or sixteen 16-bit channels");
+    constexpr int HALF = VEC / 2;
+    float lo[HALF], hi[HALF];
+    widen_row<T, HALF>(raw.lo, lo);
+    widen_row<T, HALF>(raw.hi, hi);
+#pragma unroll
+    for (int e = 0; e < HALF; ++e) {
+        v[e] = lo[e];
+        v[HALF + e] = hi[e];
     }
 }
 template <typename T, int VEC> __device__ __forceinline__ void widen_row(const uint2 raw, float (&v)[VEC]) {
