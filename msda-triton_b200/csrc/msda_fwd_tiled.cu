@@ -195,6 +195,13 @@ cudaError_t launch_forward_tiled(const KernelArgs &a, int dtype, int sm_count, c
         return cudaErrorNotSupported;
     }
     if (a.D != 32) return cudaErrorNotSupported;
+    // fp32, 9..15 points (L=3, K=4): 256-bit lanes as for 16 points (0.153 -> 0.145 ms); with more than 16 slots the
+    // wide layout (>= 6 points per lane) spills and loses (20 points: 0.229 -> 0.254 ms), 8 slots stay as they are
+    if (dtype == 0 && a.LK > 8 && a.LK < 16) {
+        const char *e = std::getenv("MSDA_B200_FWD_VARIANT");
+        if (!(e && (e[0] == '0' || e[0] == '1')))
+            return launch_tiled_cfg<float, 4, 16, 512, 2, false, true, 32>(a, sm_count, st);
+    }
     if (a.LK == 8) {
         if (dtype == 0) return launch_tiled_t<float, 8, 8>(a, sm_count, st);
         if (dtype == 1) return launch_tiled_t<__half, 4, 8>(a, sm_count, st);
