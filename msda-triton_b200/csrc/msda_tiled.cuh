@@ -63,8 +63,9 @@ struct WaveSchedule {
 //   * Backward (wave_pace_cta): the CTA does synchronise at the end of a wave; keeping its warps on ONE (b,h) slice
 //     is worth more than the drained pipelines there (B=16: 270 -> 258 us per image, B=64: 351 -> 258 us; the
 //     warp-level variant only reaches 311 us at B=64).
-//   * This is a PERFORMANCE HINT, not a correctness barrier: the wait is bounded (kPaceTimeoutCycles), so a grid
-//     that is not fully co-resident (another kernel holding SMs) only loses the pacing, it cannot deadlock.
+//   * This is a PERFORMANCE HINT, not a correctness barrier: the wait is bounded (kPaceTimeoutCycles) and the first
+//     time-out switches the pacing off for the rest of the launch, so a grid that is not fully co-resident (another
+//     kernel holding SMs, a partitioned GPU) only loses the pacing and ~130 us; it cannot deadlock.
 constexpr long long kPaceTimeoutCycles = 1ll << 18;   // ~130 us at 1.97 GHz
 constexpr int kPaceRing = 8;                          // > pace_slack + 2 waves between any two warps of a CTA
 constexpr int kPaceMaxSlack = 4;
@@ -78,7 +79,13 @@ __device__ __forceinline__ void pace_wait(const WaveSchedule &w, int wave) {
     while (true) {
         unsigned seen;
         asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(w.pace) : "memory");
-        if (seen >= target || clock64() - t0 > kPaceTimeoutCycles) break;
+        if (seen >= target) break;
+        if (clock64() - t0 > kPaceTimeoutCycles) {
+            // the grid is evidently not co-resident (or a CTA is badly delayed): switch the pacing off for the rest of
+            // this launch -- the top bit makes every later comparison succeed at once
+            atomicOr(w.pace, 0x80000000u);
+            break;
+        }
         __nanosleep(256);
     }
 }

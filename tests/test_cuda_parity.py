@@ -413,3 +413,29 @@ def test_nonfinite_points_are_memory_safe(K, Kp, pm):
     assert torch.equal(ga[0, keep.cuda()], clean[3][0, keep.cuda()])
     b = to_np(clean[1][1])
     assert_close(to_np(gi[1]), b, 1e-5, 2e-6 * np.abs(b).max(), "grad_img of the clean image")
+
+
+def test_concurrent_paced_launches_on_two_streams(K, monkeypatch):
+    """Two multi-wave (paced) launches in flight on different streams: each persistent grid finds only part of the SMs
+    free, so its CTAs are not co-resident -- pacing must degrade to a bounded wait (never a deadlock) and both results
+    must equal the serial ones."""
+    monkeypatch.setenv("MSDA_B200_SLICES_PER_WAVE", "1")
+    sets = [[t.cuda() for t in make_inputs(2, 3000, 8, 32, BENCH_PYRAMID, 4, seed=30 + i, points="wide")] for i in range(2)]
+    serial = []
+    for img, s, pts, aw, go in sets:
+        serial.append((K.b200_multi_scale_deformable_attention_fwd(img, s, pts, aw, "border", True),
+                       K.b200_multi_scale_deformable_attention_bwd(go, img, s, pts, aw, "border", True)))
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    results = [None, None]
+    for rep in range(3):
+        for i, (img, s, pts, aw, go) in enumerate(sets):
+            with torch.cuda.stream(streams[i]):
+                results[i] = (K.b200_multi_scale_deformable_attention_fwd(img, s, pts, aw, "border", True),
+                              K.b200_multi_scale_deformable_attention_bwd(go, img, s, pts, aw, "border", True))
+    torch.cuda.synchronize()
+    for (out, g), (want_out, want_g) in zip(results, serial):
+        assert torch.equal(out, want_out)
+        assert torch.equal(g[1], want_g[1]) and torch.equal(g[2], want_g[2])
+        b = to_np(want_g[0])
+        assert_close(to_np(g[0]), b, 1e-5, 2e-6 * np.abs(b).max(), "grad_img")
