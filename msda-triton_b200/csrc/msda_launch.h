@@ -35,5 +35,6 @@ cudaError_t launch_round_grad_img(void *dst, const float *src, long long n, int 
 
 // Arrival counter for wave pacing (msda_pace.cu): *slot = a device word zeroed on `st`, or nullptr when pacing is off.
 cudaError_t acquire_pace_counter(cudaStream_t st, unsigned **slot);
+bool pacing_forced();   // MSDA_B200_WAVE_PACING=2: pace every multi-wave launch, whatever the wave size (tests)
 
 }  // namespace msda

@@ -22,6 +22,11 @@ static bool pacing_enabled() {
     return !(e && e[0] == '0');
 }
 
+bool pacing_forced() {
+    const char *e = std::getenv("MSDA_B200_WAVE_PACING");   // test knob: 2 paces every multi-wave launch
+    return e && e[0] == '2';
+}
+
 cudaError_t acquire_pace_counter(cudaStream_t st, unsigned **slot) {
     static std::atomic<unsigned> ticket{0};
     static std::atomic<unsigned *> base[kMaxDevices];

@@ -382,11 +382,13 @@ def test_wave_pacing_many_waves(K, slack):
     img, s, pts, aw, go = make_inputs(2, 3000, 8, 32, BENCH_PYRAMID, 4, seed=13, points="wide")
     base = run_cuda(K, img, s, pts, aw, go, "zeros", False)
     os.environ["MSDA_B200_SLICES_PER_WAVE"] = "1"
+    os.environ["MSDA_B200_WAVE_PACING"] = "2"          # pace although these waves are small
     os.environ["MSDA_B200_PACE_SLACK"] = slack
     try:
         paced = run_cuda(K, img, s, pts, aw, go, "zeros", False)
     finally:
         os.environ.pop("MSDA_B200_SLICES_PER_WAVE")
+        os.environ.pop("MSDA_B200_WAVE_PACING")
         os.environ.pop("MSDA_B200_PACE_SLACK")
     assert torch.equal(paced[0], base[0])
     assert torch.equal(paced[2], base[2]) and torch.equal(paced[3], base[3])
@@ -420,6 +422,7 @@ def test_concurrent_paced_launches_on_two_streams(K, monkeypatch):
     free, so its CTAs are not co-resident -- pacing must degrade to a bounded wait (never a deadlock) and both results
     must equal the serial ones."""
     monkeypatch.setenv("MSDA_B200_SLICES_PER_WAVE", "1")
+    monkeypatch.setenv("MSDA_B200_WAVE_PACING", "2")               # pace although these waves are small
     sets = [[t.cuda() for t in make_inputs(2, 3000, 8, 32, BENCH_PYRAMID, 4, seed=30 + i, points="wide")] for i in range(2)]
     serial = []
     for img, s, pts, aw, go in sets:
