@@ -439,6 +439,11 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from msda_triton import _lib, kernels as K
+    numa_cores = None
+    if world > 1 and os.environ.get("MSDA_BENCH_NUMA_BIND", "1") != "0":
+        # one process per GPU: keep each rank's pinned host buffers (e2e) in the memory next to its GPU
+        from msda_triton.host import bind_host_thread_to_gpu
+        numa_cores = bind_host_thread_to_gpu(torch.device("cuda", local))
 
     def sync():
         if dist is not None:
@@ -532,6 +537,7 @@ def run_ours(args):
             "clocks": head["clocks"],
             "e2e": {"value": world * B * Q / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "host_numa_bind": bool(numa_cores),
                     "api": "msda_triton.host.HostMsda(chunks=1).run -- pinned host buffers, two staging sets, H2D of "
                            "step i+1 overlapped with kernels / D2H of step i",
                     "autograd_unpipelined": {"value": world * B * Q / (e2e_plain_ms * 1e-3),

@@ -19,6 +19,30 @@ import torch
 from . import kernels
 
 
+def bind_host_thread_to_gpu(device: Optional[torch.device] = None) -> Optional[list]:
+    """Restricts the calling process to the CPU cores NVML reports as local to ``device`` (same NUMA node / PCIe root),
+    so that pinned host buffers allocated afterwards land in the memory next to that GPU.  With one process per GPU
+    on a multi-socket host this is what keeps the per-GPU host<->device copies from all crossing the socket link.
+    Returns the core list, or None when NVML / the affinity call is unavailable (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        props = torch.cuda.get_device_properties(dev)
+        pynvml.nvmlInit()
+        bus = f"{props.pci_domain_id:08x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
+        cores = [64 * i + b for i, word in enumerate(words) for b in range(64) if (word >> b) & 1]
+        allowed = sorted(set(cores) & os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:  # noqa: BLE001 -- an optimisation only
+        return None
+
+
 class HostMsda:
     def __init__(self, batch: int, num_pixels: int, heads: int, channels: int, queries: int, levels: int, points: int,
                  dtype: torch.dtype = torch.float32, device: Optional[torch.device] = None, backward: bool = True,
