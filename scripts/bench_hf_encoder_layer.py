@@ -1,6 +1,7 @@
 """A Hugging Face Deformable-DETR encoder layer (d_model 256, 8 heads, 4 levels, 4 points; random weights) at the
 800x1333 pyramid (22 223 pixels, B=2): forward+backward with HF's own pure-PyTorch operator (grid_sample per level)
-versus this package's CUDA operator patched in (tests/test_hf_dropin_gpu.py checks that results agree).
+versus this package's CUDA operator patched in by msda_triton.integrations.patch_transformers
+(tests/test_hf_dropin_gpu.py checks that results agree).
 Run on the GPU box."""
 import os
 import sys
@@ -8,7 +9,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "msda-triton_b200"))
-import msda_triton  # noqa: E402
+from msda_triton import integrations  # noqa: E402
 from transformers import DeformableDetrConfig, ResNetConfig  # noqa: E402
 from transformers.models.deformable_detr import modeling_deformable_detr as m  # noqa: E402
 
@@ -52,22 +53,16 @@ def main():
             (out[0] if isinstance(out, tuple) else out).backward(gout)
             hidden.grad = None
 
-        def ours(self, value, value_spatial_shapes, value_spatial_shapes_list, level_start_index, sampling_locations,
-                 attention_weights, im2col_step):
-            return msda_triton.multiscale_deformable_attention(
-                value, value_spatial_shapes, sampling_locations, attention_weights, "zeros", False).flatten(2)
-
         torch.cuda.reset_peak_memory_stats()
         native = median_ms(step)
         native_mem = torch.cuda.max_memory_allocated() / 2 ** 20
-        original = m.MultiScaleDeformableAttention.forward
-        m.MultiScaleDeformableAttention.forward = ours
+        integrations.patch_transformers(["deformable_detr"])
         try:
             torch.cuda.reset_peak_memory_stats()
             patched = median_ms(step)
             patched_mem = torch.cuda.max_memory_allocated() / 2 ** 20
         finally:
-            m.MultiScaleDeformableAttention.forward = original
+            integrations.unpatch_transformers()
         print(f"{dt}: encoder layer fwd+bwd  HF operator {native:.2f} ms (peak {native_mem:.0f} MB)  ->  this package "
               f"{patched:.2f} ms (peak {patched_mem:.0f} MB)  x{native / patched:.1f}", flush=True)
 

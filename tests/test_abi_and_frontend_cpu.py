@@ -202,3 +202,32 @@ def test_bench_reference_arm_emits_contract_json():
         assert key in d
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_transformers_patch_keeps_cpu_path_and_restores():
+    """integrations.patch_transformers: CPU tensors keep Hugging Face's own operator (and agree with our CPU route);
+    unpatch restores the class."""
+    import torch
+    try:
+        from transformers.models.deformable_detr import modeling_deformable_detr as m
+    except Exception as e:  # noqa: BLE001
+        pytest.skip(f"transformers unavailable: {e}")
+    import msda_triton
+    from msda_triton import integrations
+    from util import make_inputs
+    shapes_list = [(6, 8), (3, 4)]
+    img, shapes, pts, aw, _ = make_inputs(2, 9, 4, 8, shapes_list, 3, seed=2, weights="softmax_lk")
+    level_start = torch.tensor([0, 48])
+    op = m.MultiScaleDeformableAttention()
+    before = op(img, shapes, shapes_list, level_start, pts, aw, 64)
+    original = m.MultiScaleDeformableAttention.forward
+    assert "deformable_detr" in integrations.patch_transformers(["deformable_detr", "no_such_family"])
+    try:
+        assert m.MultiScaleDeformableAttention.forward is not original
+        patched = op(img, shapes, shapes_list, level_start, pts, aw, 64)
+    finally:
+        integrations.unpatch_transformers()
+    assert m.MultiScaleDeformableAttention.forward is original
+    assert torch.equal(patched, before)
+    ours = msda_triton.multiscale_deformable_attention(img, shapes, pts, aw, "zeros", False).flatten(2)
+    torch.testing.assert_close(ours, before, rtol=1e-5, atol=1e-6)

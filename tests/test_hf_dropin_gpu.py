@@ -2,7 +2,7 @@
 the operator inside a Hugging Face model and observes identical detections).  Here: the Hugging Face
 ``DeformableDetrEncoderLayer`` (random weights, no download) runs once with its own pure-PyTorch operator
 (``grid_sample`` per level, padding_mode="zeros", align_corners=False) and once with this package's CUDA operator
-patched in; output and all gradients must agree.  Skipped when ``transformers`` cannot build the layer offline."""
+patched in by ``msda_triton.integrations.patch_transformers``; output and all gradients must agree.  Skipped when ``transformers`` cannot build the layer offline."""
 import pytest
 import torch
 
@@ -27,7 +27,6 @@ def _build_layer():
 
 
 def test_hf_deformable_detr_encoder_layer_with_our_operator():
-    import msda_triton
     m, layer = _build_layer()
     layer = layer.cuda().train()
     with torch.no_grad():   # HF initialises the offset bias to a fixed grid; spread the offsets over a few pixels
@@ -57,21 +56,22 @@ def test_hf_deformable_detr_encoder_layer_with_our_operator():
 
     want = run()
 
+    from msda_triton import integrations, kernels
     calls = {"n": 0}
+    real = kernels.b200_multi_scale_deformable_attention_fwd
 
-    def our_operator(self, value, value_spatial_shapes, value_spatial_shapes_list, level_start_index,
-                     sampling_locations, attention_weights, im2col_step):
+    def counting(*args, **kwargs):
         calls["n"] += 1
-        out = msda_triton.multiscale_deformable_attention(
-            value, value_spatial_shapes, sampling_locations, attention_weights, "zeros", False)
-        return out.flatten(2)                                   # [B, N, H, C] -> [B, N, H*C] as HF returns it
+        return real(*args, **kwargs)
 
-    original = m.MultiScaleDeformableAttention.forward
-    m.MultiScaleDeformableAttention.forward = our_operator
+    kernels.b200_multi_scale_deformable_attention_fwd = counting
+    assert "deformable_detr" in integrations.patch_transformers()
     try:
         got = run()
     finally:
-        m.MultiScaleDeformableAttention.forward = original
-    assert calls["n"] == 1
+        integrations.unpatch_transformers()
+        kernels.b200_multi_scale_deformable_attention_fwd = real
+    assert calls["n"] == 1                                  # the layer went through the CUDA operator
+    assert m.MultiScaleDeformableAttention.forward.__name__ == "forward"          # and the original is back
     for a, b in zip(got, want):
         torch.testing.assert_close(a, b, rtol=2e-4, atol=2e-4 * float(b.abs().max()))
