@@ -2,6 +2,7 @@
 without a GPU), the Python surface matches the reference's names / signatures / state_dict keys, the CPU-tensor route
 agrees with the oracle, and the CUDA route refuses to run without CUDA tensors."""
 import ctypes
+import os
 import inspect
 import re
 from pathlib import Path
@@ -231,3 +232,35 @@ def test_transformers_patch_keeps_cpu_path_and_restores():
     assert torch.equal(patched, before)
     ours = msda_triton.multiscale_deformable_attention(img, shapes, pts, aw, "zeros", False).flatten(2)
     torch.testing.assert_close(ours, before, rtol=1e-5, atol=1e-6)
+
+
+def test_missing_library_fails_loudly():
+    """No CPU / torch fallback for the CUDA path: without libmsda_b200.so the first library use raises."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    pkg = Path(__file__).resolve().parent.parent / "msda-triton_b200"
+    code = (
+        "import sys; sys.path.insert(0, sys.argv[1])\n"
+        "import msda_triton\n"
+        "from msda_triton import _lib\n"
+        "try:\n"
+        "    _lib.get_lib()\n"
+        "except _lib.MsdaLibraryError as e:\n"
+        "    assert 'no fallback' in str(e); print('raised')\n"
+    )
+    env = dict(os.environ, MSDA_B200_LIB="/nonexistent/libmsda_b200.so")
+    out = subprocess.run([sys.executable, "-c", code, str(pkg)], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip() == "raised", out.stderr[-2000:]
+
+
+def test_product_package_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under msda-triton_b200/ imports, loads or mentions a path into it."""
+    from pathlib import Path
+    pkg = Path(__file__).resolve().parent.parent / "msda-triton_b200"
+    offenders = []
+    for path in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")) + list(pkg.rglob("*.h")):
+        text = path.read_text()
+        if "import oracle" in text or "from oracle" in text or "msda_oracle" in text or "oracle/" in text:
+            offenders.append(str(path))
+    assert not offenders, offenders
