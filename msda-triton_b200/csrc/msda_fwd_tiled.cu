@@ -181,7 +181,8 @@ cudaError_t launch_forward_tiled(const KernelArgs &a, int dtype, int sm_count, c
             // warp iteration covers 8 units -- half the load, shuffle and address instructions per unit of the
             // 8 lanes x 128-bit layout.  Measured (bench border / zeros / DETR encoder): 0.141 / 0.141 / 0.166 ms
             // versus 0.148 / 0.154 / 0.172 ms (no gain for 256-byte fp32 rows or 128-byte 16-bit rows, which stay on
-            // 128-bit lanes).  MSDA_B200_FWD_VARIANT=0|1 select the 128-bit layouts (measurement).
+            // 128-bit lanes).  512 threads x 2-point batches is the best launch shape of those tried (640 x 2, 640 x 1,
+            // 384 x 4: 0.145-0.148 / 0.146-0.159 / 0.168-0.209 ms).  MSDA_B200_FWD_VARIANT=0|1 select the 128-bit layouts.
             const char *e = std::getenv("MSDA_B200_FWD_VARIANT");
             const bool wide = !(e && (e[0] == '0' || e[0] == '1'));
             if (a.D == 32) {
