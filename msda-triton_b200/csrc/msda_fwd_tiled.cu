@@ -3,6 +3,7 @@
 // Per warp iteration: G = 32/LANES units.  Each lane resolves PPL = LK/LANES points, then the group walks the LK
 // points in batches of NB: 5 shuffles + 4 independent 128-bit gathers per point, 4*NB gathers in flight per lane on
 // top of whatever the compiler hoists from the next batch.
+#include <cstdint>
 #include <cstdlib>
 
 #include "msda_common.cuh"
@@ -184,7 +185,8 @@ cudaError_t launch_forward_tiled(const KernelArgs &a, int dtype, int sm_count, c
             // 128-bit lanes).  512 threads x 2-point batches is the best launch shape of those tried (640 x 2, 640 x 1,
             // 384 x 4: 0.145-0.148 / 0.146-0.159 / 0.168-0.209 ms).  MSDA_B200_FWD_VARIANT=0|1 select the 128-bit layouts.
             const char *e = std::getenv("MSDA_B200_FWD_VARIANT");
-            const bool wide = !(e && (e[0] == '0' || e[0] == '1'));
+            // (256-bit loads need a 32-byte aligned pyramid; the ABI only demands 16)
+            const bool wide = !(e && (e[0] == '0' || e[0] == '1')) && reinterpret_cast<uintptr_t>(a.img) % 32 == 0;
             if (a.D == 32) {
                 if (wide) return launch_tiled_cfg<float, 4, 16, 512, 2, false, false, 32>(a, sm_count, st);
                 return launch_tiled_t<float, 8, 16>(a, sm_count, st);
@@ -202,7 +204,7 @@ cudaError_t launch_forward_tiled(const KernelArgs &a, int dtype, int sm_count, c
     if (a.D != 32) return cudaErrorNotSupported;
     // fp32, 9..15 points (L=3, K=4): 256-bit lanes as for 16 points (0.153 -> 0.145 ms); with more than 16 slots the
     // wide layout (>= 6 points per lane) spills and loses (20 points: 0.229 -> 0.254 ms), 8 slots stay as they are
-    if (dtype == 0 && a.LK > 8 && a.LK < 16) {
+    if (dtype == 0 && a.LK > 8 && a.LK < 16 && reinterpret_cast<uintptr_t>(a.img) % 32 == 0) {
         const char *e = std::getenv("MSDA_B200_FWD_VARIANT");
         if (!(e && (e[0] == '0' || e[0] == '1')))
             return launch_tiled_cfg<float, 4, 16, 512, 2, false, true, 32>(a, sm_count, st);
@@ -235,7 +237,7 @@ cudaError_t launch_module_forward_tiled(const KernelArgs &a, int dtype, int sm_c
     if (a.D == 32) {
         if (dtype == 0) {
             const char *e = std::getenv("MSDA_B200_FWD_VARIANT");
-            if (!(e && (e[0] == '0' || e[0] == '1')))
+            if (!(e && (e[0] == '0' || e[0] == '1')) && reinterpret_cast<uintptr_t>(a.img) % 32 == 0)
                 return launch_tiled_cfg<float, 4, 16, 512, 2, true, false, 32>(a, sm_count, st);
             return launch_tiled_cfg<float, 8, 16, 1024, 2, true>(a, sm_count, st);
         }

@@ -442,3 +442,20 @@ def test_concurrent_paced_launches_on_two_streams(K, monkeypatch):
         assert torch.equal(g[1], want_g[1]) and torch.equal(g[2], want_g[2])
         b = to_np(want_g[0])
         assert_close(to_np(g[0]), b, 1e-5, 2e-6 * np.abs(b).max(), "grad_img")
+
+
+@pytest.mark.parametrize("Kp", [4, 3], ids=["lk16", "lk12"])
+def test_pyramid_aligned_to_16_but_not_32_bytes(K, oracle, Kp):
+    """The C ABI asks for 16-byte alignment; the fp32 forward's 256-bit row loads need 32 and must step aside for a
+    pyramid that only has 16 (a view 4 floats into a storage)."""
+    img, s, pts, aw, go = make_inputs(2, 300, 8, 32, BENCH_PYRAMID, Kp, seed=17, points="wide")
+    flat = torch.empty(img.numel() + 4, device="cuda")
+    flat[4:] = img.cuda().reshape(-1)
+    img16 = flat[4:].view(img.shape)
+    assert img16.data_ptr() % 32 == 16 and img16.is_contiguous()
+    out = K.b200_multi_scale_deformable_attention_fwd(img16, s.cuda(), pts.cuda(), aw.cuda(), "border", False)
+    gi, gp, ga = K.b200_multi_scale_deformable_attention_bwd(go.cuda(), img16, s.cuda(), pts.cuda(), aw.cuda(),
+                                                             "border", False)
+    torch.cuda.synchronize()
+    ref = (oracle.forward(img, s, pts, aw, "border", False),) + oracle.backward(go, img, s, pts, aw, "border", False)
+    check_against((out, gi, gp, ga), ref, torch.float32, "16-byte aligned pyramid")
