@@ -3,14 +3,19 @@
 // The reference's backward adds into grad_img with tl.atomic_add (src/msda_triton/kernels.py:549-553), so the fp32
 // summation order -- and therefore the low bits of grad_img -- changes from run to run.  This path produces
 // bit-identical grad_img on every run:
-//   1. keys   : every bilinear corner (unit, point, corner) emits key = destination row (b, pixel, h) and
-//               value = its own index; invalid (zeros-mode, out-of-range) corners get the sentinel key B*Npix*H (one past
-//               the last row), so only ceil(log2(rows+1)) key bits need sorting.
+//   1. keys   : every bilinear corner (unit, point, corner) emits key = destination row (b, pixel, h), value = its own
+//               index, and its scalar weight (attention weight x bilinear weight) into a side array indexed by that
+//               value; invalid (zeros-mode, out-of-range) corners get the sentinel key B*Npix*H (one past the last
+//               row), so only ceil(log2(rows+1)) key bits need sorting.
 //   2. sort   : stable LSD radix sort by key (cub::DeviceRadixSort, deterministic), so inside a segment the
 //               contributions are ordered by (unit, point, corner).
-//   3. reduce : one lane group per destination row walks its segment IN THAT ORDER, recomputes the corner weight
-//               from the sampling point, and accumulates weight * grad_out[unit] in registers; the row is written
-//               once with a plain store (no zero-fill, no atomics, one rounding to the storage dtype).
+//   3. starts : one pass over the sorted keys records where each destination row's segment begins.
+//   4. reduce : one warp per destination row walks its segment IN THAT ORDER and accumulates
+//               weight[value] * grad_out[unit] in registers; the row is written once with a plain store (no
+//               zero-fill, no atomics, one rounding to the storage dtype).
+// (The first version recomputed the corner weight from the sampling point in step 4 and found the segment by binary
+// search: 1.05 ms for the reduce on the bench shape; with the weights precomputed and the start table it is a gather
+// of grad_out rows and an FMA per contribution: 0.64 ms, the whole deterministic backward 1.84 -> 1.43 ms.)
 // grad_sampling_points / grad_attention_weights never needed atomics and come from the regular backward kernel.
 #include <cub/device/device_radix_sort.cuh>
 
@@ -22,13 +27,15 @@ namespace msda {
 
 template <typename T>
 __global__ void __launch_bounds__(256) det_keys_kernel(const KernelArgs a, unsigned *__restrict__ keys,
-                                                       unsigned *__restrict__ vals, const long long n_points,
-                                                       const unsigned sentinel) {
+                                                       unsigned *__restrict__ vals,
+                                                       typename Traits<T>::CT *__restrict__ wts,
+                                                       const long long n_points, const unsigned sentinel) {
     using CT = typename Traits<T>::CT;
     extern __shared__ __align__(16) unsigned char s_raw[];
     Level *s_lv = reinterpret_cast<Level *>(s_raw);
     build_level_table(s_lv, a.shapes, a.L);
     const T *__restrict__ pts = static_cast<const T *>(a.pts);
+    const T *__restrict__ aw = static_cast<const T *>(a.aw);
     const bool border = a.border != 0, align = a.align != 0;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_points; i += stride) {
@@ -43,6 +50,7 @@ __global__ void __launch_bounds__(256) det_keys_kernel(const KernelArgs a, unsig
         const int step_x = (t.pack >> kPackDxBit) & 1;
         const unsigned mask = (unsigned)(t.pack >> kPackMaskShift) & 0xFu;
         const int rows[4] = {t.row00, t.row00 + step_x, t.row00 + step_y, t.row00 + step_y + step_x};
+        const CT w_att = Traits<T>::to_ct(aw[i]);
         uint4 k4, v4;
         unsigned *kk = reinterpret_cast<unsigned *>(&k4), *vv = reinterpret_cast<unsigned *>(&v4);
 #pragma unroll
@@ -50,47 +58,54 @@ __global__ void __launch_bounds__(256) det_keys_kernel(const KernelArgs a, unsig
             const unsigned long long key = ((unsigned long long)b * a.Npix + rows[c]) * a.H + h;
             kk[c] = ((mask >> c) & 1u) ? (unsigned)key : sentinel;
             vv[c] = (unsigned)(4 * i + c);
+            const CT wx = (c & 1) ? t.dx : (CT)1 - t.dx;
+            const CT wy = (c & 2) ? t.dy : (CT)1 - t.dy;
+            wts[4 * i + c] = w_att * (wy * wx);
         }
         reinterpret_cast<uint4 *>(keys)[i] = k4;
         reinterpret_cast<uint4 *>(vals)[i] = v4;
     }
 }
 
+// starts[r] = index of the first sorted contribution of destination row r (rows without contributions keep kNoStart).
+constexpr unsigned kNoStart = 0xFFFFFFFFu;
+
+__global__ void __launch_bounds__(256) det_starts_kernel(const unsigned *__restrict__ keys, unsigned *__restrict__ starts,
+                                                         const long long n, const unsigned n_rows) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned k = keys[i];
+        if (k < n_rows && (i == 0 || keys[i - 1] != k)) starts[k] = (unsigned)i;
+    }
+}
+
 // One WARP per destination row.  The warp's 32/lanes lane groups take the row's contributions round-robin (group t
 // handles positions lo+t, lo+t+T, ... of the sorted segment, two at a time for memory-level parallelism); the group
 // partials are then combined by a fixed butterfly, so the summation order depends only on the sorted order.
+// Rows are visited in memory order: neighbouring rows own neighbouring segments of the sorted arrays (visiting them in
+// a scattered order to spread the long segments of the coarsest level over the grid was 1.8x SLOWER, and fetching the
+// (value, weight) pairs of a block with one coalesced load + shuffles made no difference: 0.67 vs 0.64 ms).
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) det_reduce_kernel(const KernelArgs a, const unsigned *__restrict__ keys,
-                                                         const unsigned *__restrict__ vals, const long long n,
+                                                         const unsigned *__restrict__ vals,
+                                                         const typename Traits<T>::CT *__restrict__ wts,
+                                                         const unsigned *__restrict__ starts, const long long n,
                                                          const long long n_rows) {
     using CT = typename Traits<T>::CT;
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    Level *s_lv = reinterpret_cast<Level *>(s_raw);
-    build_level_table(s_lv, a.shapes, a.L);
-    const T *__restrict__ pts = static_cast<const T *>(a.pts);
-    const T *__restrict__ aw = static_cast<const T *>(a.aw);
     const T *__restrict__ gout = static_cast<const T *>(a.gout);
     T *__restrict__ gimg = static_cast<T *>(a.gimg);
     const int lanes = a.lanes;
     const int lane = threadIdx.x & 31;
     const int j = lane & (lanes - 1);
     const int team = lane / lanes, teams = 32 / lanes;
-    const bool border = a.border != 0, align = a.align != 0;
     const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long warps_total = ((long long)gridDim.x * blockDim.x) >> 5;
+    const unsigned points4 = 4u * (unsigned)a.LK;   // contributions per unit
 
     auto contribution = [&](long long i, int c0, CT (&acc)[VEC]) {
         const unsigned v = vals[i];
-        const int c = (int)(v & 3u);
-        const long long pi = (long long)(v >> 2);  // (unit, point) index
-        const long long u = pi / a.LK;
-        const int p = (int)(pi - u * a.LK);
-        CT xy[2];
-        load_vec<T, 2>(pts + 2 * pi, xy);
-        const Tap<CT> t = locate<CT>(xy[0], xy[1], s_lv[p / a.K], border, align);
-        const CT wx = (c & 1) ? t.dx : (CT)1 - t.dx;
-        const CT wy = (c & 2) ? t.dy : (CT)1 - t.dy;
-        const CT w = Traits<T>::to_ct(aw[pi]) * (wy * wx);
+        const CT w = wts[v];
+        const unsigned u = v / points4;               // unit (b, q, h) the contribution comes from
         CT go[VEC];
         load_vec<T, VEC>(gout + (size_t)u * a.D + c0, go);
 #pragma unroll
@@ -98,13 +113,9 @@ __global__ void __launch_bounds__(256) det_reduce_kernel(const KernelArgs a, con
     };
 
     for (long long r = warp_global; r < n_rows; r += warps_total) {
-        // lower_bound(keys, r): first contribution of this row (every lane searches redundantly)
-        long long lo = 0, hi = n;
+        const unsigned first = starts[r];
         const unsigned key = (unsigned)r;
-        while (lo < hi) {
-            const long long mid = (lo + hi) >> 1;
-            if (keys[mid] < key) lo = mid + 1; else hi = mid;
-        }
+        const long long lo = first == kNoStart ? n : (long long)first;
         for (int chunk = 0; chunk < a.chunks; ++chunk) {
             const int c0 = (chunk * lanes + j) * VEC;
             const bool c_live = c0 < a.D;
@@ -145,9 +156,13 @@ size_t det_sort_temp_bytes(long long n) {
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// layout: keys_in | keys_out | vals_in | vals_out | weights (8 bytes per contribution reserved: fp64 problems) |
+//         row starts | cub temp
 size_t det_workspace_bytes(const KernelArgs &a) {
     const long long n = a.units * a.LK * 4;
-    return 4 * align_up((size_t)n * sizeof(unsigned), 256) + align_up(det_sort_temp_bytes(n), 256);
+    const long long n_rows = (long long)a.B * a.Npix * a.H;
+    return 4 * align_up((size_t)n * sizeof(unsigned), 256) + align_up((size_t)n * sizeof(double), 256) +
+           align_up((size_t)n_rows * sizeof(unsigned), 256) + align_up(det_sort_temp_bytes(n), 256);
 }
 
 bool det_supported(const KernelArgs &a) {
@@ -164,28 +179,38 @@ static cudaError_t launch_det_t(const KernelArgs &a, int vec, void *workspace, i
     unsigned char *ws = static_cast<unsigned char *>(workspace);
     unsigned *keys_in = reinterpret_cast<unsigned *>(ws), *keys_out = reinterpret_cast<unsigned *>(ws + arr);
     unsigned *vals_in = reinterpret_cast<unsigned *>(ws + 2 * arr), *vals_out = reinterpret_cast<unsigned *>(ws + 3 * arr);
-    void *temp = ws + 4 * arr;
+    using CT = typename Traits<T>::CT;
+    CT *wts = reinterpret_cast<CT *>(ws + 4 * arr);
+    const size_t wts_bytes = align_up((size_t)n * sizeof(double), 256);
+    unsigned *starts = reinterpret_cast<unsigned *>(ws + 4 * arr + wts_bytes);
+    const size_t starts_bytes = align_up((size_t)n_rows * sizeof(unsigned), 256);
+    void *temp = ws + 4 * arr + wts_bytes + starts_bytes;
     size_t temp_bytes = det_sort_temp_bytes(n);
     const size_t smem = sizeof(Level) * (size_t)a.L;
 
     int key_bits = 1;
     while (key_bits < 32 && (1ull << key_bits) <= (unsigned long long)n_rows) ++key_bits;   // keys in [0, n_rows]
-    det_keys_kernel<T><<<grid_for(n_points, 256, sm_count), 256, smem, st>>>(a, keys_in, vals_in, n_points,
+    det_keys_kernel<T><<<grid_for(n_points, 256, sm_count), 256, smem, st>>>(a, keys_in, vals_in, wts, n_points,
                                                                            (unsigned)n_rows);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, n, 0, key_bits, st);
     if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(starts, 0xFF, (size_t)n_rows * sizeof(unsigned), st);
+    if (e != cudaSuccess) return e;
+    det_starts_kernel<<<grid_for(n, 256, sm_count), 256, 0, st>>>(keys_out, starts, n, (unsigned)n_rows);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
     const int grid = grid_for(n_rows, 256 / 32, sm_count);   // one warp per destination row
     switch (vec) {
         case 8:
-            if constexpr (Traits<T>::kMaxVec >= 8) det_reduce_kernel<T, 8><<<grid, 256, smem, st>>>(a, keys_out, vals_out, n, n_rows);
+            if constexpr (Traits<T>::kMaxVec >= 8) det_reduce_kernel<T, 8><<<grid, 256, 0, st>>>(a, keys_out, vals_out, wts, starts, n, n_rows);
             break;
         case 4:
-            if constexpr (Traits<T>::kMaxVec >= 4) det_reduce_kernel<T, 4><<<grid, 256, smem, st>>>(a, keys_out, vals_out, n, n_rows);
+            if constexpr (Traits<T>::kMaxVec >= 4) det_reduce_kernel<T, 4><<<grid, 256, 0, st>>>(a, keys_out, vals_out, wts, starts, n, n_rows);
             break;
-        case 2: det_reduce_kernel<T, 2><<<grid, 256, smem, st>>>(a, keys_out, vals_out, n, n_rows); break;
-        default: det_reduce_kernel<T, 1><<<grid, 256, smem, st>>>(a, keys_out, vals_out, n, n_rows); break;
+        case 2: det_reduce_kernel<T, 2><<<grid, 256, 0, st>>>(a, keys_out, vals_out, wts, starts, n, n_rows); break;
+        default: det_reduce_kernel<T, 1><<<grid, 256, 0, st>>>(a, keys_out, vals_out, wts, starts, n, n_rows); break;
     }
     return cudaGetLastError();
 }
