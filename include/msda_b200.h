@@ -27,9 +27,13 @@
  *     therefore CUDA-graph capturable.
  *   - Return value: 0 on success, a negative MSDA_ERR_* code on invalid arguments, a positive cudaError_t value if
  *     a CUDA call failed.  msda_last_error() returns a thread-local, human-readable description of the last failure.
- *   - Thread safety: the library is stateless apart from the thread-local error string and a per-device cache of
- *     immutable device properties; it may be called concurrently from several host threads (autograd calls backward
- *     from its own thread).
+ *   - Thread safety: the library may be called concurrently from several host threads (autograd calls backward from
+ *     its own thread).  Its state: the thread-local error string; a per-device cache of immutable device properties;
+ *     the measurement / test knobs read ONCE from the environment (MSDA_B200_*, see msda_reload_tuning); and a ring of
+ *     256 device words ("pace counters", msda_pace.cu) from which a launch that walks several L2-sized waves takes the
+ *     next one and zeroes it on its stream.  A captured CUDA graph keeps the counter it was captured with; a replay
+ *     that overlaps other multi-wave launches whose ticket wrapped onto the same word may pass a wave early or sit
+ *     out one bounded wait (~130 us) -- results are unaffected (the pacing is a performance hint only).
  */
 #ifndef MSDA_B200_H_
 #define MSDA_B200_H_
@@ -91,6 +95,15 @@ typedef struct msda_problem {
 
 int msda_abi_version(void);
 const char *msda_last_error(void);
+
+/*
+ * The library reads its measurement / test knobs (environment variables MSDA_B200_FORCE_GENERIC, _SLICES_PER_WAVE,
+ * _PACE_SLACK, _WAVE_PACING, _FWD_VARIANT, _BWD_SPLIT, _SPLIT_SLOTS, _BWD_OWNER, _OWNER_ROWS, _OWNER_WORKERS,
+ * _DET_VARIANT) once, at the first call that needs them, never on the launch path.  A process that changes one of them
+ * afterwards calls this to have them read again.  No reference counterpart (the reference's only knob is Triton's
+ * autotuner, kernels.py:259-265).
+ */
+void msda_reload_tuning(void);
 
 /*
  * Forward: out[b,q,h,:] = sum_{l,k} w[b,q,h,l,k] * bilinear(img_l[b,:,h,:], p[b,q,h,l,k])

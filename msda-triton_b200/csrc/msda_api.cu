@@ -11,6 +11,7 @@
 #include "msda_common.cuh"
 #include "msda_launch.h"
 #include "msda_tiled.cuh"
+#include "msda_tuning.h"
 
 namespace {
 
@@ -122,10 +123,7 @@ void fill_args(msda::KernelArgs &a, const msda_problem *p, int vec) {
 }
 
 // Debug / test switch: MSDA_B200_FORCE_GENERIC=1 routes every problem to the generic kernels.
-bool force_generic() {
-    const char *e = std::getenv("MSDA_B200_FORCE_GENERIC");
-    return e && e[0] && e[0] != '0';
-}
+bool force_generic() { return msda::tuning().force_generic != 0; }
 
 }  // namespace
 
@@ -134,6 +132,8 @@ extern "C" {
 int msda_abi_version(void) { return MSDA_B200_ABI_VERSION; }
 
 const char *msda_last_error(void) { return g_err; }
+
+void msda_reload_tuning(void) { msda::reload_tuning(); }
 
 int msda_forward(void *out, const void *img, const int64_t *img_shapes, const void *sampling_points,
                  const void *attention_weights, const msda_problem *prob, void *stream) {
@@ -160,8 +160,9 @@ int msda_forward(void *out, const void *img, const int64_t *img_shapes, const vo
     a.out = out;
 
     cudaError_t e = cudaErrorNotSupported;
+    // the tuned forward reads up to 4 attention weights (fp32: 16 bytes) and 8 coordinates per lane access
     const bool tiled_ok = !force_generic() && vec * es == 16 && aligned(sampling_points, 16) &&
-                          aligned(attention_weights, 8);
+                          aligned(attention_weights, 16);
     if (tiled_ok) e = msda::launch_forward_tiled(a, prob->dtype, dev.sm_count, st);
     if (e == cudaErrorNotSupported) e = msda::launch_forward_generic(a, prob->dtype, vec, dev.sm_count, st);
     if (e != cudaSuccess) return fail_cuda(e, "msda_forward launch");

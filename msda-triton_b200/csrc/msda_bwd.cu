@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(256) msda_bwd_generic_kernel(const KernelArgs 
     using CT = typename Traits<T>::CT;
     extern __shared__ __align__(16) unsigned char s_raw[];
     Level *s_lv = reinterpret_cast<Level *>(s_raw);
-    build_level_table(s_lv, a.shapes, a.L);
+    if (!build_level_table(s_lv, a.shapes, a.L, a.Npix)) return;
 
     const T *__restrict__ img = static_cast<const T *>(a.img);
     const T *__restrict__ pts = static_cast<const T *>(a.pts);

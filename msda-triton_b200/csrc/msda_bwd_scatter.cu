@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     __shared__ BinLevel s_bl[kMaxBinLevels];
     __shared__ int s_bin[3];  // first binned point, number of binned levels, number of list heads
 
-    build_level_table(s_lv, a.shapes, a.L);
+    if (!build_level_table(s_lv, a.shapes, a.L, a.Npix)) return;
     if (threadIdx.x == 0) {
         // binned levels: the longest suffix (coarsest first) that fits MAXHEADS list heads and NBP points per unit
         int heads = 0, l0 = a.L, n_bl = 0;
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                 const int step_y = t.pack & kPackDyMask;
                 const int step_x = (t.pack >> kPackDxBit) & 1;
                 const unsigned mask = (unsigned)(t.pack >> kPackMaskShift) & 0xFu;
-                const float wl = tu.live ? wa[pp] : 0.0f;
+                const float wl = wa[pp];   // padding queries add nothing: their row adds are predicated on tu.live
                 const float wy1 = wl * t.dy, wy0 = wl - wy1;
                 float w4[4];
                 w4[1] = wy0 * t.dx;
@@ -196,7 +196,8 @@ __global__ void __launch_bounds__(THREADS, 1)
                         float gv[VEC];
 #pragma unroll
                         for (int e = 0; e < VEC; ++e) gv[e] = go[e] * w4[c];
-                        if (BORDER || ((mask >> c) & 1u)) red_add_vec<VEC>(gimg_lane + (size_t)rows4[c] * row_stride, gv);
+                        if (tu.live && (BORDER || ((mask >> c) & 1u)))
+                            red_add_vec<VEC>(gimg_lane + (size_t)rows4[c] * row_stride, gv);
                     }
                 }
             }

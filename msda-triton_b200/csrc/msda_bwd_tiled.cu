@@ -31,22 +31,6 @@ template <int VEC, int LANES> __device__ __forceinline__ void red_add_row(float 
     static_assert(VEC == 4 || VEC == 8, "tuned kernels use 128-bit lanes");
 }
 
-template <int N, int STEP> __device__ __forceinline__ void transpose_reduce(float (&part)[N], const int j) {
-    // lanes with bit STEP clear keep the lower half, their partners (j ^ STEP) the upper half
-    constexpr int HALF = N / 2;
-    const bool upper = (j & STEP) != 0;
-#pragma unroll
-    for (int k = 0; k < HALF; ++k) {
-        const float keep = upper ? part[k + HALF] : part[k];
-        const float send = upper ? part[k] : part[k + HALF];
-        part[k] = keep + __shfl_xor_sync(0xffffffffu, send, STEP);
-    }
-    if constexpr (STEP > 1) {
-        float(&lower)[HALF] = reinterpret_cast<float(&)[HALF]>(part);
-        transpose_reduce<HALF, STEP / 2>(lower, j);
-    }
-}
-
 // FUSED = backward of the module core: operands are the raw projection + reference points (see msda_tiled.cuh);
 // the epilogue turns (grad weight, grad point) into grad of the projection triples (softmax backward, 1/shape or
 // ref_wh/2K scaling) and accumulates grad of the reference points with a handful of scalar atomics per unit.
@@ -65,7 +49,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     static_assert(LANES % NB == 0, "batch must divide the group");
 
     __shared__ Level s_lv[8];   // tuned kernels take L <= 8
-    build_level_table(s_lv, a.shapes, a.L);
+    if (!build_level_table(s_lv, a.shapes, a.L, a.Npix)) return;
 
     const T *__restrict__ img = static_cast<const T *>(a.img);
     const T *__restrict__ gout = static_cast<const T *>(a.gout);
@@ -112,8 +96,8 @@ __global__ void __launch_bounds__(THREADS, 1)
         // fp32 accumulation row of this (b,h): for 16-bit storage (VEC == 8) the row is kept in the PERMUTED channel
         // order of accum_position() so that each red.v4 instruction of a lane group covers whole 32-byte sectors
         unsigned char *__restrict__ gimg_base = reinterpret_cast<unsigned char *>(gimg + tu.bh_off + j * 4);
-        // padding queries of the last tile shadow a real query: their image contributions are scaled to zero
-        const float live_scale = tu.live ? 1.0f : 0.0f;
+        // padding queries of the last tile shadow a real query: they gather like it but add nothing to grad_img
+        const bool live = tu.live;
         const int p0 = SPLIT ? tu.p0 : 0;   // first point of this tile's sub-unit
 
         TileTap tap[PPL];
@@ -147,7 +131,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                     const unsigned pack = __shfl_sync(0xffffffffu, tap[pp].pack, src, LANES);
                     fx[n] = __shfl_sync(0xffffffffu, tap[pp].dx, src, LANES);
                     fy[n] = __shfl_sync(0xffffffffu, tap[pp].dy, src, LANES);
-                    fw[n] = __shfl_sync(0xffffffffu, op.wa[pp], src, LANES) * live_scale;
+                    fw[n] = __shfl_sync(0xffffffffu, op.wa[pp], src, LANES);
                     corner_offsets(off, pack, row_bytes, o[n]);
                     msk[n] = BORDER ? 0xFu : ((pack >> kPackMaskShift) & 0xFu);
                     // always in range (clamped rows); zeros padding is applied to the dot products below
@@ -178,7 +162,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll
                             for (int e = 0; e < VEC; ++e) gv[e] = go[e] * s;
                             float *dst = reinterpret_cast<float *>(gimg_base + (size_t)o[n][c] * kAccScale);
-                            if (alive && (BORDER || ((msk[n] >> c) & 1u))) red_add_row<VEC, LANES>(dst, gv);
+                            if (live && alive && (BORDER || ((msk[n] >> c) & 1u))) red_add_row<VEC, LANES>(dst, gv);
                         }
                     }
                     const int pidx = (jj0 + n) * PPL + pp;
@@ -352,7 +336,7 @@ template <typename T> static cudaError_t launch_split(const KernelArgs &a, int s
         // ragged: the slot count that wastes fewer dead slots (20 points: 3 x 8 rather than 2 x 16; 0.91 vs 1.10 ms)
         const int dead16 = (a.LK + 15) / 16 * 16 - a.LK, dead8 = (a.LK + 7) / 8 * 8 - a.LK;
         bool use8 = dead8 <= dead16;   // tie: 8 slots measured faster (28 points: 0.89 vs 0.94 ms)
-        if (const char *e = std::getenv("MSDA_B200_SPLIT_SLOTS")) use8 = std::atoi(e) == 8;   // tuning knob
+        if (tuning().split_slots > 0) use8 = tuning().split_slots == 8;   // tuning knob
         if (use8) return launch_split_t<T, 8, 8, true>(a, sm_count, st);
         return launch_split_t<T, 8, 16, true>(a, sm_count, st);
     }
@@ -380,9 +364,17 @@ cudaError_t launch_module_backward_tiled(const KernelArgs &a, int dtype, int sm_
 // 0.47 ms fused (profiles/r1_ncu_summary.md section 4), so it is opt-in.
 constexpr int kMaxSplitPoints = 128;
 
-static bool split_backward_enabled() {
-    const char *e = std::getenv("MSDA_B200_BWD_SPLIT");
-    return e && e[0] && e[0] != '0';
+static bool split_backward_enabled() { return tuning().bwd_split != 0; }
+
+// Owner-warp backward (msda_bwd_owner.cu): worth it when grad_img is wanted, the pyramid is small enough for its coarse
+// level(s) to fit the shared-memory accumulator (the shapes live on the device, so Npix of a 4x-per-level pyramid
+// stands in: coarsest level ~ Npix / 85), and every worker warp gets enough tiles to amortise the per-CTA set-up and
+// the warp given up to the owner.  MSDA_B200_BWD_OWNER=0|1 overrides.
+static bool owner_backward_wanted(const KernelArgs &a, int sm_count) {
+    if (!(a.flags & kNeedImg)) return false;
+    if (tuning().bwd_owner >= 0) return tuning().bwd_owner != 0;
+    const long long tiles = (long long)a.B * a.H * ((a.Q + 3) / 4);
+    return a.Npix <= 32768 && tiles >= 8LL * 15 * sm_count;
 }
 
 cudaError_t launch_backward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st) {
@@ -435,7 +427,13 @@ cudaError_t launch_backward_tiled(const KernelArgs &a, int dtype, int sm_count, 
         return launch_tiled_t<float, 8, 16>(k2, sm_count, st);
     }
     if (dtype == 0) {
-        if (a.D == 32) return launch_tiled_t<float, 8, 16>(a, sm_count, st);
+        if (a.D == 32) {
+            if (owner_backward_wanted(a, sm_count)) {
+                const cudaError_t e = launch_backward_owner(a, dtype, sm_count, st);
+                if (e != cudaErrorNotSupported) return e;
+            }
+            return launch_tiled_t<float, 8, 16>(a, sm_count, st);
+        }
         if (a.D == 64) return launch_tiled_t<float, 16, 16>(a, sm_count, st);
     } else if (dtype == 1) {
         if (a.D == 32) return launch_tiled_t<__half, 8, 16, false, 4>(a, sm_count, st);

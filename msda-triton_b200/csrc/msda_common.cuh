@@ -50,20 +50,28 @@ struct __align__(16) Level {
 
 // Builds the level table in shared memory once per CTA (the reference redoes this in every one of its B*Q*H
 // programs, kernels.py:290).  Works for any L: a single thread runs the exclusive prefix sum, L is tiny.
-__device__ __forceinline__ void build_level_table(Level *s_lv, const long long *__restrict__ shapes, int L) {
+// Returns false (for every thread of the CTA) when the device-side shapes do not describe the pyramid the caller
+// announced -- a level with h <= 0 or w <= 0, or sum h*w > Npix (fewer rows than the image holds are harmless).  The reference trusts the table blindly
+// (kernels.py:52-62); here a mismatch would turn into out-of-bounds gathers and row adds, so the kernels return
+// without touching memory instead (the check is one compare per CTA; s_lv[0].pad carries the verdict).
+__device__ __forceinline__ bool build_level_table(Level *s_lv, const long long *__restrict__ shapes, int L, int Npix) {
     if (threadIdx.x == 0) {
-        int run = 0;
+        long long run = 0;
+        bool ok = true;
         for (int l = 0; l < L; ++l) {
-            const int h = (int)shapes[2 * l + 0];
-            const int w = (int)shapes[2 * l + 1];
-            s_lv[l].h = h;
-            s_lv[l].w = w;
-            s_lv[l].off = run;
+            const long long h = shapes[2 * l + 0];
+            const long long w = shapes[2 * l + 1];
+            ok = ok && h > 0 && w > 0 && h <= Npix && w <= Npix;
+            s_lv[l].h = (int)h;
+            s_lv[l].w = (int)w;
+            s_lv[l].off = (int)run;
             s_lv[l].pad = 0;
-            run += h * w;
+            run += ok ? h * w : 0;
         }
+        s_lv[0].pad = (ok && run <= (long long)Npix) ? 1 : 0;
     }
     __syncthreads();
+    return s_lv[0].pad != 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     __shared__ Level s_lv[8];   // tuned kernels take L <= 8
     __shared__ unsigned s_pace[kPaceRing];
     if (threadIdx.x < kPaceRing) s_pace[threadIdx.x] = 0;
-    build_level_table(s_lv, a.shapes, a.L);
+    if (!build_level_table(s_lv, a.shapes, a.L, a.Npix)) return;
 
     const T *__restrict__ img = static_cast<const T *>(a.img);
     T *__restrict__ out = static_cast<T *>(a.out);
@@ -160,9 +160,7 @@ static cudaError_t launch_tiled_cfg(const KernelArgs &a, int sm_count, cudaStrea
 template <typename T, int LANES, int LK, bool PADDED = false>
 static cudaError_t launch_tiled_t(const KernelArgs &a, int sm_count, cudaStream_t st) {
     if constexpr (!PADDED) {
-        if (const char *e = std::getenv("MSDA_B200_FWD_VARIANT")) {   // tuning knob
-            if (e[0] == '1') return launch_tiled_cfg<T, LANES, LK, 512, 4>(a, sm_count, st);
-        }
+        if (tuning().fwd_variant == 1) return launch_tiled_cfg<T, LANES, LK, 512, 4>(a, sm_count, st);   // tuning knob
     }
     // lanes that own >= 3 points keep more state: stay at 128 registers there
     if constexpr (TiledCfg<T, LANES, LK>::PPL >= 3)
@@ -184,9 +182,8 @@ cudaError_t launch_forward_tiled(const KernelArgs &a, int dtype, int sm_count, c
             // versus 0.148 / 0.154 / 0.172 ms (no gain for 256-byte fp32 rows or 128-byte 16-bit rows, which stay on
             // 128-bit lanes).  512 threads x 2-point batches is the best launch shape of those tried (640 x 2, 640 x 1,
             // 384 x 4: 0.145-0.148 / 0.146-0.159 / 0.168-0.209 ms).  MSDA_B200_FWD_VARIANT=0|1 select the 128-bit layouts.
-            const char *e = std::getenv("MSDA_B200_FWD_VARIANT");
             // (256-bit loads need a 32-byte aligned pyramid; the ABI only demands 16)
-            const bool wide = !(e && (e[0] == '0' || e[0] == '1')) && reinterpret_cast<uintptr_t>(a.img) % 32 == 0;
+            const bool wide = tuning().fwd_variant < 0 && reinterpret_cast<uintptr_t>(a.img) % 32 == 0;
             if (a.D == 32) {
                 if (wide) return launch_tiled_cfg<float, 4, 16, 512, 2, false, false, 32>(a, sm_count, st);
                 return launch_tiled_t<float, 8, 16>(a, sm_count, st);
@@ -205,9 +202,7 @@ cudaError_t launch_forward_tiled(const KernelArgs &a, int dtype, int sm_count, c
     // fp32, 9..15 points (L=3, K=4): 256-bit lanes as for 16 points (0.153 -> 0.145 ms); with more than 16 slots the
     // wide layout (>= 6 points per lane) spills and loses (20 points: 0.229 -> 0.254 ms), 8 slots stay as they are
     if (dtype == 0 && a.LK > 8 && a.LK < 16 && reinterpret_cast<uintptr_t>(a.img) % 32 == 0) {
-        const char *e = std::getenv("MSDA_B200_FWD_VARIANT");
-        if (!(e && (e[0] == '0' || e[0] == '1')))
-            return launch_tiled_cfg<float, 4, 16, 512, 2, false, true, 32>(a, sm_count, st);
+        if (tuning().fwd_variant < 0) return launch_tiled_cfg<float, 4, 16, 512, 2, false, true, 32>(a, sm_count, st);
     }
     if (a.LK == 8) {
         if (dtype == 0) return launch_tiled_t<float, 8, 8>(a, sm_count, st);
@@ -236,8 +231,7 @@ cudaError_t launch_module_forward_tiled(const KernelArgs &a, int dtype, int sm_c
     if (a.LK != 16 || a.L > 8 || (a.ref_dim != 2 && a.ref_dim != 4)) return cudaErrorNotSupported;
     if (a.D == 32) {
         if (dtype == 0) {
-            const char *e = std::getenv("MSDA_B200_FWD_VARIANT");
-            if (!(e && (e[0] == '0' || e[0] == '1')) && reinterpret_cast<uintptr_t>(a.img) % 32 == 0)
+            if (tuning().fwd_variant < 0 && reinterpret_cast<uintptr_t>(a.img) % 32 == 0)
                 return launch_tiled_cfg<float, 4, 16, 512, 2, true, false, 32>(a, sm_count, st);
             return launch_tiled_cfg<float, 8, 16, 1024, 2, true>(a, sm_count, st);
         }

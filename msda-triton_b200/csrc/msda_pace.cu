@@ -9,6 +9,7 @@
 #include <cstdlib>
 
 #include "msda_launch.h"
+#include "msda_tuning.h"
 
 namespace msda {
 
@@ -17,15 +18,9 @@ constexpr int kMaxDevices = 64;
 
 __device__ unsigned g_pace_ring[kPaceSlots];
 
-static bool pacing_enabled() {
-    const char *e = std::getenv("MSDA_B200_WAVE_PACING");   // measurement knob: 0 disables
-    return !(e && e[0] == '0');
-}
+static bool pacing_enabled() { return tuning().wave_pacing != 0; }   // measurement knob: 0 disables
 
-bool pacing_forced() {
-    const char *e = std::getenv("MSDA_B200_WAVE_PACING");   // test knob: 2 paces every multi-wave launch
-    return e && e[0] == '2';
-}
+bool pacing_forced() { return tuning().wave_pacing == 2; }   // test knob: 2 paces every multi-wave launch
 
 cudaError_t acquire_pace_counter(cudaStream_t st, unsigned **slot) {
     static std::atomic<unsigned> ticket{0};

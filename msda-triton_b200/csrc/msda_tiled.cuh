@@ -19,6 +19,7 @@
 #include <type_traits>
 
 #include "msda_common.cuh"
+#include "msda_tuning.h"
 
 namespace msda {
 
@@ -127,19 +128,13 @@ inline WaveSchedule make_wave_schedule(const KernelArgs &a, int tiles_per_bh, si
     long long images = (long long)(l2_budget_bytes / (image_bytes ? image_bytes : 1));
     if (images < 1) images = 1;
     long long max_slices = images * a.H;
-    if (const char *e = std::getenv("MSDA_B200_SLICES_PER_WAVE")) {   // tuning knob
-        const long n = std::atol(e);
-        if (n > 0) max_slices = n;
-    }
+    if (tuning().slices_per_wave > 0) max_slices = tuning().slices_per_wave;   // tuning knob
     if (max_slices > w.slices) max_slices = w.slices;
     w.waves = (int)((w.slices + max_slices - 1) / max_slices);
     w.slices_per_wave = (int)max_slices;
     w.pace = nullptr;
-    w.pace_slack = 1;
-    if (const char *e = std::getenv("MSDA_B200_PACE_SLACK")) {   // tuning knob
-        const int n = std::atoi(e);
-        w.pace_slack = n < 0 ? 0 : (n > kPaceMaxSlack ? kPaceMaxSlack : n);
-    }
+    const int slack = tuning().pace_slack;   // tuning knob
+    w.pace_slack = slack < 0 ? 0 : (slack > kPaceMaxSlack ? kPaceMaxSlack : slack);
     return w;
 }
 
@@ -406,6 +401,25 @@ template <typename T, int VEC> __device__ __forceinline__ void widen_row(const u
     static_assert(sizeof(T) == 2 && VEC == 4, "8-byte slices hold four 16-bit channels");
     widen_word<T>(raw.x, v[0], v[1]);
     widen_word<T>(raw.y, v[2], v[3]);
+}
+
+// Transposing butterfly over the LANES lanes of a group (backward kernels): every step halves the values a lane keeps,
+// so reducing N partials costs N*(1 - 1/LANES) shuffles instead of N*log2(LANES), and lane j ends with exactly the
+// points it loaded in part[0 .. N/LANES).  Call with STEP = LANES / 2.
+template <int N, int STEP> __device__ __forceinline__ void transpose_reduce(float (&part)[N], const int j) {
+    // lanes with bit STEP clear keep the lower half, their partners (j ^ STEP) the upper half
+    constexpr int HALF = N / 2;
+    const bool upper = (j & STEP) != 0;
+#pragma unroll
+    for (int k = 0; k < HALF; ++k) {
+        const float keep = upper ? part[k + HALF] : part[k];
+        const float send = upper ? part[k] : part[k + HALF];
+        part[k] = keep + __shfl_xor_sync(0xffffffffu, send, STEP);
+    }
+    if constexpr (STEP > 1) {
+        float(&lower)[HALF] = reinterpret_cast<float(&)[HALF]>(part);
+        transpose_reduce<HALF, STEP / 2>(lower, j);
+    }
 }
 
 }  // namespace msda

@@ -1,0 +1,25 @@
+// msda_tuning.h -- measurement / test knobs of libmsda_b200.so, read from the environment ONCE (first use) instead of on
+// every launch.  msda_reload_tuning() (C ABI) re-reads them; tests that flip a knob in-process call it afterwards.
+#pragma once
+
+namespace msda {
+
+struct Tuning {
+    int force_generic = 0;     // MSDA_B200_FORCE_GENERIC=1    : every problem takes the generic kernels
+    int slices_per_wave = 0;   // MSDA_B200_SLICES_PER_WAVE=n  : (b,h) slices per L2 wave (0 = sized to L2)
+    int pace_slack = 1;        // MSDA_B200_PACE_SLACK=n       : waves a CTA may run ahead of the slowest CTA
+    int wave_pacing = 1;       // MSDA_B200_WAVE_PACING=0|1|2  : off | auto | pace every multi-wave launch
+    int fwd_variant = -1;      // MSDA_B200_FWD_VARIANT=0|1    : 128-bit forward layouts (default: 256-bit lanes)
+    int bwd_split = 0;         // MSDA_B200_BWD_SPLIT=1        : split backward (tuned kernel + scatter kernel)
+    int split_slots = 0;       // MSDA_B200_SPLIT_SLOTS=8|16   : slot count of ragged sub-unit backward launches
+    int bwd_owner = -1;        // MSDA_B200_BWD_OWNER=0|1      : coarse levels accumulated in shared memory by an owner
+                               //                                warp (default: chosen per problem)
+    int owner_rows = 0;        // MSDA_B200_OWNER_ROWS=n       : accumulator capacity in pyramid rows (0 = default)
+    int owner_workers = 0;     // MSDA_B200_OWNER_WORKERS=14|15: worker warps beside the owner warp (0 = default)
+    int det_variant = -1;      // MSDA_B200_DET_VARIANT=0|1    : deterministic grad_img: 0 = radix sort, 1 = slice binning
+};
+
+const Tuning &tuning();
+void reload_tuning();
+
+}  // namespace msda

@@ -42,6 +42,8 @@ def _load() -> ctypes.CDLL:
     lib.msda_abi_version.argtypes = []
     lib.msda_last_error.restype = ctypes.c_char_p
     lib.msda_last_error.argtypes = []
+    lib.msda_reload_tuning.restype = None
+    lib.msda_reload_tuning.argtypes = []
     lib.msda_forward.restype = ci
     lib.msda_forward.argtypes = [vp, vp, vp, vp, vp, pp, vp]
     lib.msda_backward_workspace_bytes.restype = sz
@@ -75,6 +77,11 @@ def get_lib() -> ctypes.CDLL:
     if _lib_handle is None:
         _lib_handle = _load()
     return _lib_handle
+
+
+def reload_tuning() -> None:
+    """Has the library re-read its MSDA_B200_* knobs from the environment (it reads them once, at first use)."""
+    get_lib().msda_reload_tuning()
 
 
 def check(rc: int, what: str) -> None:

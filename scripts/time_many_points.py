@@ -6,7 +6,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "msda-triton_b200"))
-from msda_triton import kernels as K  # noqa: E402
+from msda_triton import _lib, kernels as K  # noqa: E402
 
 SHAPES = {
     "5 levels down to 4x4, K=4": ([(64, 64), (32, 32), (16, 16), (8, 8), (4, 4)], 4),   # 16-pixel level: hot-spot bound
@@ -50,11 +50,13 @@ def main():
             row = {}
             for generic in ("0", "1"):
                 os.environ["MSDA_B200_FORCE_GENERIC"] = generic
+                _lib.reload_tuning()   # the library reads its knobs once
                 row["fwd" + generic] = median_ms(
                     lambda: K.b200_multi_scale_deformable_attention_fwd(img, shapes, pts, aw, "border", True), flush)
                 row["bwd" + generic] = median_ms(
                     lambda: K.b200_multi_scale_deformable_attention_bwd(go, img, shapes, pts, aw, "border", True), flush)
             os.environ.pop("MSDA_B200_FORCE_GENERIC")
+            _lib.reload_tuning()
             print(f"{dt} {name}: fwd tuned {row['fwd0']:.3f} generic {row['fwd1']:.3f} ms | "
                   f"bwd tuned {row['bwd0']:.3f} generic {row['bwd1']:.3f} ms", flush=True)
 

@@ -19,3 +19,16 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(autouse=True)
+def _library_knobs_follow_the_environment():
+    """libmsda_b200 reads its MSDA_B200_* knobs once; tests that flip one call util.knobs() / _lib.reload_tuning().
+    After every test (monkeypatch has restored the environment by then) the library re-reads them."""
+    yield
+    try:
+        from msda_triton import _lib
+    except Exception:
+        return
+    if _lib._lib_handle is not None:
+        _lib.reload_tuning()

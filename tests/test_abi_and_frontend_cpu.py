@@ -35,7 +35,7 @@ def test_header_declares_the_expected_entry_points():
     assert declared_symbols() == sorted([
         "msda_abi_version", "msda_last_error", "msda_forward", "msda_backward_workspace_bytes", "msda_backward",
         "msda_level_table", "msda_probe_gather", "msda_probe_scatter", "msda_module_supported", "msda_module_forward",
-        "msda_module_backward"])
+        "msda_module_backward", "msda_reload_tuning"])
 
 
 def test_library_exports_every_declared_symbol(libpath):

@@ -135,6 +135,8 @@ def test_cuda_graph_capture_of_a_paced_multi_wave_launch(monkeypatch):
     from msda_triton import kernels as K
     monkeypatch.setenv("MSDA_B200_SLICES_PER_WAVE", "1")           # 16 waves on a full persistent grid
     monkeypatch.setenv("MSDA_B200_WAVE_PACING", "2")               # pace although these waves are small
+    from msda_triton import _lib
+    _lib.reload_tuning()
     img, s, pts, aw, go = (t.cuda() for t in make_inputs(2, 3000, 8, 32, BENCH_PYRAMID, 4, seed=14))
     eager_out = K.b200_multi_scale_deformable_attention_fwd(img, s, pts, aw, "zeros", False)
     eager_g = K.b200_multi_scale_deformable_attention_bwd(go, img, s, pts, aw, "zeros", False)

@@ -13,7 +13,7 @@ import pytest
 import torch
 
 from conftest import GOLDEN
-from util import BENCH_PYRAMID, DETR_PYRAMID, assert_close, make_inputs, to_np
+from util import BENCH_PYRAMID, DETR_PYRAMID, assert_close, knobs, make_inputs, to_np
 
 pytestmark = pytest.mark.gpu
 
@@ -141,11 +141,8 @@ def test_tuned_equals_generic(K, pm, ac, Kp):
     only summation order differs."""
     img, s, pts, aw, go = make_inputs(2, 500, 8, 32, BENCH_PYRAMID, Kp, seed=3, points="wide")
     tuned = run_cuda(K, img, s, pts, aw, go, pm, ac)
-    os.environ["MSDA_B200_FORCE_GENERIC"] = "1"
-    try:
+    with knobs(MSDA_B200_FORCE_GENERIC="1"):
         generic = run_cuda(K, img, s, pts, aw, go, pm, ac)
-    finally:
-        os.environ.pop("MSDA_B200_FORCE_GENERIC")
     for a, b, what in zip(tuned, generic, ("out", "grad_img", "grad_points", "grad_weights")):
         b = to_np(b)
         assert_close(to_np(a), b, 1e-5, 2e-6 * max(1.0, np.abs(b).max()), what)
@@ -336,12 +333,9 @@ def test_deterministic_full_size_bitwise(K):
 def test_split_backward_variant(K, oracle, pm, ac):
     """The opt-in split backward (K1 without grad_img + scatter-only K2 with in-CTA binning) must match the oracle."""
     img, s, pts, aw, go = make_inputs(2, 700, 8, 32, BENCH_PYRAMID, 4, seed=17, points="wide", weights="softmax_lk")
-    os.environ["MSDA_B200_BWD_SPLIT"] = "1"
-    try:
+    with knobs(MSDA_B200_BWD_SPLIT="1"):
         test = run_cuda(K, img, s, pts, aw, go, pm, ac)
         only_img = run_cuda(K, img, s, pts, aw, go, pm, ac, needs=(True, False, False))
-    finally:
-        os.environ.pop("MSDA_B200_BWD_SPLIT")
     ref = (oracle.forward(img, s, pts, aw, pm, ac),) + oracle.backward(go, img, s, pts, aw, pm, ac)
     check_against(test, ref, torch.float32, "split backward")
     assert_close(to_np(only_img[1]), ref[1], 1e-4, 1e-5 * np.abs(ref[1]).max(), "split backward, grad_img only")
@@ -381,15 +375,9 @@ def test_wave_pacing_many_waves(K, slack):
     same forward bits and the same gradients as the single-wave schedule."""
     img, s, pts, aw, go = make_inputs(2, 3000, 8, 32, BENCH_PYRAMID, 4, seed=13, points="wide")
     base = run_cuda(K, img, s, pts, aw, go, "zeros", False)
-    os.environ["MSDA_B200_SLICES_PER_WAVE"] = "1"
-    os.environ["MSDA_B200_WAVE_PACING"] = "2"          # pace although these waves are small
-    os.environ["MSDA_B200_PACE_SLACK"] = slack
-    try:
+    # pace although these waves are small
+    with knobs(MSDA_B200_SLICES_PER_WAVE="1", MSDA_B200_WAVE_PACING="2", MSDA_B200_PACE_SLACK=slack):
         paced = run_cuda(K, img, s, pts, aw, go, "zeros", False)
-    finally:
-        os.environ.pop("MSDA_B200_SLICES_PER_WAVE")
-        os.environ.pop("MSDA_B200_WAVE_PACING")
-        os.environ.pop("MSDA_B200_PACE_SLACK")
     assert torch.equal(paced[0], base[0])
     assert torch.equal(paced[2], base[2]) and torch.equal(paced[3], base[3])
     b = to_np(base[1])
@@ -423,6 +411,8 @@ def test_concurrent_paced_launches_on_two_streams(K, monkeypatch):
     must equal the serial ones."""
     monkeypatch.setenv("MSDA_B200_SLICES_PER_WAVE", "1")
     monkeypatch.setenv("MSDA_B200_WAVE_PACING", "2")               # pace although these waves are small
+    from msda_triton import _lib
+    _lib.reload_tuning()
     sets = [[t.cuda() for t in make_inputs(2, 3000, 8, 32, BENCH_PYRAMID, 4, seed=30 + i, points="wide")] for i in range(2)]
     serial = []
     for img, s, pts, aw, go in sets:

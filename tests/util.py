@@ -80,3 +80,32 @@ def check_module_against_golden(g, module, inputs, shapes, rtol, atol_scale, max
     for name, p in module.named_parameters():
         ref = g[f"grad.{name}"]
         assert_close(to_np(p.grad), ref, rtol, atol_scale * np.abs(ref).max(), f"grad {name}", max_outliers)
+
+
+class knobs:
+    """with knobs(MSDA_B200_FORCE_GENERIC="1"): ...  -- sets library knobs in the environment and has the library
+    re-read them (it reads the environment once, not per launch); restores both on exit."""
+
+    def __init__(self, **env):
+        self.env = {k: str(v) for k, v in env.items()}
+        self.saved = {}
+
+    def __enter__(self):
+        import os
+        from msda_triton import _lib
+        for k, v in self.env.items():
+            self.saved[k] = os.environ.get(k)
+            os.environ[k] = v
+        _lib.reload_tuning()
+        return self
+
+    def __exit__(self, *exc):
+        import os
+        from msda_triton import _lib
+        for k, old in self.saved.items():
+            if old is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = old
+        _lib.reload_tuning()
+        return False
