@@ -279,20 +279,24 @@ class MultiscaleDeformableAttention(nn.Module):
 
         # CUDA fast path: softmax, sampling-point arithmetic and the operator in one kernel (no materialised
         # sampling_points / attention_weights).  Set MSDA_B200_FUSED_MODULE=0 to take the composed path below.
-        if (value.is_cuda and _fused_module_enabled()
+        # Operand precision follows the composed path below (= the reference, frontend.py:268-283): under autocast the
+        # operator runs in fp32 (custom_fwd(cast_inputs=float32)) on sampling points computed as fp32 anchor + offsets,
+        # so the fused core gets fp32 operands too -- the anchors are never rounded to the 16-bit autocast dtype.
+        # Mixed dtypes outside autocast (e.g. a bf16 module fed fp32 anchors) take the composed path.
+        autocast = value.is_cuda and torch.is_autocast_enabled("cuda")
+        fusable = autocast or reference_points.dtype == value.dtype
+        if (value.is_cuda and fusable and _fused_module_enabled()
                 and not kernels.is_deterministic()):   # the bit-reproducible grad_img lives on the composed path
-            ref = reference_points.to(value.dtype)
+            ref = reference_points
+            if autocast:
+                value, projected, ref = value.float(), projected.float(), reference_points.float()
             if img_shapes.device != value.device:
                 img_shapes = img_shapes.to(value.device, non_blocking=True)
             if torch.compiler.is_compiling():
                 # traced programs: the same kernels behind torch.library custom ops (no graph break)
                 if kernels.module_core_supported_static(value, projected, ref):
                     from .ops import module_core_op
-                    operands = (value, projected, ref)
-                    if torch.is_autocast_enabled("cuda"):   # the eager Function runs in fp32 under autocast
-                        operands = tuple(t.float() for t in operands)
-                    out = module_core_op(operands[0], img_shapes, operands[1], operands[2], self.padding_mode,
-                                         self.align_corners)
+                    out = module_core_op(value, img_shapes, projected, ref, self.padding_mode, self.align_corners)
                     return self.query_output_proj(out.reshape(batch, num_queries, self.hidden_dim))
             elif kernels.module_core_supported(value, projected, ref):
                 out = fused_module_core(value, img_shapes, projected, ref, self.padding_mode, self.align_corners)

@@ -102,6 +102,44 @@ def test_module_fused_equals_composed_cuda(coords, dtype, hidden):
                      max_outliers=max(8, int(frac * b.size)))
 
 
+@pytest.mark.parametrize("amp", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+@pytest.mark.parametrize("coords", [2, 4])
+def test_module_under_autocast_fused_equals_composed(amp, coords):
+    """AMP training (fp32 module and inputs under torch.autocast): the reference keeps the reference points in fp32
+    (anchor + offsets promotes, frontend.py:268-283) and runs the operator in fp32 (custom_fwd cast_inputs).  The fused
+    core must sample the SAME locations: its operands are widened to fp32, never narrowed to the autocast dtype --
+    rounding an fp32 anchor to bf16 moves it by up to 2^-9, i.e. 0.1-0.3 px on the 64-167 px levels."""
+    from msda_triton import MultiscaleDeformableAttention
+    torch.manual_seed(11)
+    emb, heads, levels, points = 256, 8, 4, 4
+    npix = sum(h * w for h, w in BENCH_PYRAMID)
+    img = torch.randn(2, npix, emb, device="cuda")
+    queries = torch.randn(2, 300, emb, device="cuda")
+    ref_pts = torch.rand(2, 300, coords, device="cuda") * 0.8 + 0.1     # fp32 anchors with bits below bf16 precision
+    shapes = torch.tensor(BENCH_PYRAMID, device="cuda")
+    module = MultiscaleDeformableAttention(emb, emb, levels, heads, points, "border", True).cuda()
+
+    def run(fused):
+        os.environ["MSDA_B200_FUSED_MODULE"] = "1" if fused else "0"
+        try:
+            i, q, r = (t.clone().requires_grad_(True) for t in (img, queries, ref_pts))
+            module.zero_grad()
+            with torch.autocast("cuda", dtype=amp):
+                out = module(i, shapes, q, r)
+            out.float().square().sum().backward()
+            return [out.detach().float(), i.grad, q.grad, r.grad]
+        finally:
+            os.environ.pop("MSDA_B200_FUSED_MODULE")
+
+    got, want = run(True), run(False)
+    # both paths see the same autocast-rounded projections and the same fp32 anchors: they differ only by fp32
+    # summation order (and the rare floor-boundary tie in the offset gradients)
+    for a, b, what in zip(got, want, ("out", "grad_img", "grad_queries", "grad_reference_points")):
+        b = to_np(b)
+        assert_close(to_np(a), b, 2e-3, 2e-3 * max(1e-3, np.abs(b).max()), f"autocast {what}",
+                     max_outliers=max(8, int(2e-3 * b.size)))
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
 @pytest.mark.parametrize("coords", [2, 4])
 @pytest.mark.parametrize("D", [32, 64])
