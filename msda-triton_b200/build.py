@@ -53,7 +53,8 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     def compile_one(src: Path) -> Path:
         obj = OBJ_DIR / (src.stem + ".o")
         if force or _stale(obj, [src, *headers]):
-            cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+            extra = os.environ.get("MSDA_B200_NVCC_EXTRA", "").split()   # e.g. -DMSDA_TMEM_PROF (debug builds only)
+            cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", str(src), "-o", str(obj)]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
                 print(" ".join(cmd), flush=True)

@@ -366,15 +366,14 @@ constexpr int kMaxSplitPoints = 128;
 
 static bool split_backward_enabled() { return tuning().bwd_split != 0; }
 
-// Owner-warp backward (msda_bwd_owner.cu): worth it when grad_img is wanted, the pyramid is small enough for its coarse
-// level(s) to fit the shared-memory accumulator (the shapes live on the device, so Npix of a 4x-per-level pyramid
-// stands in: coarsest level ~ Npix / 85), and every worker warp gets enough tiles to amortise the per-CTA set-up and
-// the warp given up to the owner.  MSDA_B200_BWD_OWNER=0|1 overrides.
-static bool owner_backward_wanted(const KernelArgs &a, int sm_count) {
+// Tensor-memory backward (msda_bwd_tmem.cu): OPT-IN (MSDA_B200_BWD_TMEM=1).  It removes 25-50 % of the row adds, but the
+// per-record tensor-memory read-modify-write costs ~280 clk inside this kernel (50 clk in isolation), which puts
+// ~10k clk of serial work on every warp tile and loses against the row adds it saves (bench shape: 0.93 ms against
+// 0.47 ms; profiles/r2_tmem_backward.md has the measurements).
+static bool tmem_backward_wanted(const KernelArgs &a, int sm_count) {
+    (void)sm_count;
     if (!(a.flags & kNeedImg)) return false;
-    if (tuning().bwd_owner >= 0) return tuning().bwd_owner != 0;
-    const long long tiles = (long long)a.B * a.H * ((a.Q + 3) / 4);
-    return a.Npix <= 32768 && tiles >= 8LL * 15 * sm_count;
+    return tuning().bwd_tmem > 0;
 }
 
 cudaError_t launch_backward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st) {
@@ -428,8 +427,8 @@ cudaError_t launch_backward_tiled(const KernelArgs &a, int dtype, int sm_count, 
     }
     if (dtype == 0) {
         if (a.D == 32) {
-            if (owner_backward_wanted(a, sm_count)) {
-                const cudaError_t e = launch_backward_owner(a, dtype, sm_count, st);
+            if (tmem_backward_wanted(a, sm_count)) {
+                const cudaError_t e = launch_backward_tmem(a, dtype, sm_count, st);
                 if (e != cudaErrorNotSupported) return e;
             }
             return launch_tiled_t<float, 8, 16>(a, sm_count, st);

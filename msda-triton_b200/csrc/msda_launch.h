@@ -20,9 +20,9 @@ cudaError_t launch_backward_tiled(const KernelArgs &a, int dtype, int sm_count, 
 cudaError_t launch_module_forward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st);
 cudaError_t launch_module_backward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st);
 
-// Tuned backward with the coarse pyramid levels accumulated in shared memory by an owner warp (msda_bwd_owner.cu):
-// fp32, D == 32, L == 4, K == 4, grad_img requested.  cudaErrorNotSupported otherwise.
-cudaError_t launch_backward_owner(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st);
+// Tuned backward with the coarse pyramid levels accumulated in tensor memory (msda_bwd_tmem.cu):
+// fp32, D == 32, L*K == 16, K == 4, grad_img requested.  cudaErrorNotSupported otherwise.
+cudaError_t launch_backward_tmem(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st);
 
 // grad_img alone, without gathers (split backward; msda_bwd_scatter.cu).  a.gimg = zero-filled fp32 accumulation image.
 cudaError_t launch_backward_scatter(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st);

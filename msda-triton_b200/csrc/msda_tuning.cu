@@ -27,9 +27,9 @@ void read_env() {
     t.fwd_variant = env_int("MSDA_B200_FWD_VARIANT", -1);
     t.bwd_split = env_int("MSDA_B200_BWD_SPLIT", 0) != 0;
     t.split_slots = env_int("MSDA_B200_SPLIT_SLOTS", 0);
-    t.bwd_owner = env_int("MSDA_B200_BWD_OWNER", -1);
-    t.owner_rows = env_int("MSDA_B200_OWNER_ROWS", 0);
-    t.owner_workers = env_int("MSDA_B200_OWNER_WORKERS", 0);
+    t.bwd_tmem = env_int("MSDA_B200_BWD_TMEM", -1);
+    t.tmem_levels = env_int("MSDA_B200_TMEM_LEVELS", 2);
+    t.tmem_warps = env_int("MSDA_B200_TMEM_WARPS", 15);
     t.det_variant = env_int("MSDA_B200_DET_VARIANT", -1);
     g_tuning = t;
 }

@@ -12,10 +12,10 @@ struct Tuning {
     int fwd_variant = -1;      // MSDA_B200_FWD_VARIANT=0|1    : 128-bit forward layouts (default: 256-bit lanes)
     int bwd_split = 0;         // MSDA_B200_BWD_SPLIT=1        : split backward (tuned kernel + scatter kernel)
     int split_slots = 0;       // MSDA_B200_SPLIT_SLOTS=8|16   : slot count of ragged sub-unit backward launches
-    int bwd_owner = -1;        // MSDA_B200_BWD_OWNER=0|1      : coarse levels accumulated in shared memory by an owner
-                               //                                warp (default: chosen per problem)
-    int owner_rows = 0;        // MSDA_B200_OWNER_ROWS=n       : accumulator capacity in pyramid rows (0 = default)
-    int owner_workers = 0;     // MSDA_B200_OWNER_WORKERS=14|15: worker warps beside the owner warp (0 = default)
+    int bwd_tmem = -1;         // MSDA_B200_BWD_TMEM=0|1       : coarse levels accumulated in tensor memory
+                               //                                (msda_bwd_tmem.cu; default: chosen per problem)
+    int tmem_warps = 15;       // MSDA_B200_TMEM_WARPS=12|15   : warps per CTA of the tensor-memory backward
+    int tmem_levels = 2;       // MSDA_B200_TMEM_LEVELS=0|1|2  : at most this many of the coarsest levels go to tensor memory
     int det_variant = -1;      // MSDA_B200_DET_VARIANT=0|1    : deterministic grad_img: 0 = radix sort, 1 = slice binning
 };
 

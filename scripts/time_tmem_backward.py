@@ -1,7 +1,7 @@
-"""A/B timing of the owner-warp backward (csrc/msda_bwd_owner.cu) against the plain tuned backward: cold L2, CUDA events,
-medians.  Knob combinations: MSDA_B200_BWD_OWNER (0/1), MSDA_B200_OWNER_ROWS (accumulator capacity), MSDA_B200_OWNER_WORKERS.
+"""A/B timing of the tensor-memory backward (csrc/msda_bwd_tmem.cu) against the plain tuned backward: cold L2, CUDA
+events, medians.  Knobs: MSDA_B200_BWD_TMEM (0/1), MSDA_B200_TMEM_LEVELS (0/1/2).
 
-    python scripts/time_owner_backward.py [workload ...] [--json gpurun_out/owner_timing.json]
+    python scripts/time_tmem_backward.py [workload ...] [--json gpurun_out/tmem_timing.json]
 """
 import json
 import os
@@ -36,14 +36,15 @@ def timeit(fn, reps=30, warm=4):
 
 
 VARIANTS = [
-    ("plain", {"MSDA_B200_BWD_OWNER": "0"}),
-    ("owner_rows320_w15", {"MSDA_B200_BWD_OWNER": "1", "MSDA_B200_OWNER_ROWS": "320", "MSDA_B200_OWNER_WORKERS": "15"}),
-    ("owner_rows320_w14", {"MSDA_B200_BWD_OWNER": "1", "MSDA_B200_OWNER_ROWS": "320", "MSDA_B200_OWNER_WORKERS": "14"}),
-    ("owner_rows64_w15", {"MSDA_B200_BWD_OWNER": "1", "MSDA_B200_OWNER_ROWS": "64", "MSDA_B200_OWNER_WORKERS": "15"}),
-    ("owner_rows273_w15", {"MSDA_B200_BWD_OWNER": "1", "MSDA_B200_OWNER_ROWS": "273", "MSDA_B200_OWNER_WORKERS": "15"}),
+    ("plain", {"MSDA_B200_BWD_TMEM": "0"}),
+    ("tmem_levels0", {"MSDA_B200_BWD_TMEM": "1", "MSDA_B200_TMEM_LEVELS": "0"}),
+    ("tmem_levels1", {"MSDA_B200_BWD_TMEM": "1", "MSDA_B200_TMEM_LEVELS": "1"}),
+    ("tmem_levels2", {"MSDA_B200_BWD_TMEM": "1", "MSDA_B200_TMEM_LEVELS": "2"}),
+    ("tmem_levels0_w12", {"MSDA_B200_BWD_TMEM": "1", "MSDA_B200_TMEM_LEVELS": "0", "MSDA_B200_TMEM_WARPS": "12"}),
+    ("tmem_levels2_w12", {"MSDA_B200_BWD_TMEM": "1", "MSDA_B200_TMEM_LEVELS": "2", "MSDA_B200_TMEM_WARPS": "12"}),
     ("auto", {}),
 ]
-KNOBS = ("MSDA_B200_BWD_OWNER", "MSDA_B200_OWNER_ROWS", "MSDA_B200_OWNER_WORKERS")
+KNOBS = ("MSDA_B200_BWD_TMEM", "MSDA_B200_TMEM_LEVELS", "MSDA_B200_TMEM_WARPS")
 
 out_json = None
 names = []
@@ -68,11 +69,8 @@ for name in names:
             os.environ.pop(k, None)
         os.environ.update(env)
         _lib.reload_tuning()
-        for needs_label, needs in (("all", (1, 1, 1)), ("img_pts", (1, 1, 0))):
-            if needs_label != "all" and label not in ("plain", "owner_rows320_w15"):
-                continue
-            row[f"{label}/{needs_label}"] = round(timeit(lambda: K.b200_multi_scale_deformable_attention_bwd(
-                t["go"], t["img"], s, t["pts"], t["aw"], pm, ac, needs=needs, deterministic=False)), 4)
+        row[label] = round(timeit(lambda: K.b200_multi_scale_deformable_attention_bwd(
+            t["go"], t["img"], s, t["pts"], t["aw"], pm, ac, needs=(1, 1, 1), deterministic=False)), 4)
     for k in KNOBS:
         os.environ.pop(k, None)
     _lib.reload_tuning()
