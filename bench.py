@@ -9,7 +9,10 @@ scripts/benchmark.py:25-31): B=4 images per GPU, Q=10 000 queries, H=8, D=32, L=
 padding_mode="border", align_corners=True, synthetic seeded inputs (img~N(0,1), points~U[0,1), weights=softmax(N(0,1))
 over K, grad_out~U[0,1)).  One STEP = one forward + one backward (all three gradients) over that batch.
 Multi-GPU: the path shards by batch with no data-path collective, every rank owns B=4 images -> weak
-scaling; value = all ranks' queries / max-over-ranks device time.
+scaling; value = all ranks' queries / max-over-ranks device time.  At EVERY N the line also carries (extra.*):
+the B=64 encoder training shape batch-sharded 64/N images per rank (strong scaling), the DETR encoder B=2
+query-sharded over all N ranks with the grad_img reduce-scatter (checked against the unsharded operator in the
+warm-up), a pinned-memcpy duplex probe run by all ranks at once (the host-side ceiling of `e2e`), and the CPU baseline.
 
 Timing: every step is bracketed by CUDA events on the launching stream; a 256 MiB buffer is overwritten between
 steps OUTSIDE the event pair so each step starts with a cold L2 (the reference's do_bench does the same).  The K steps
@@ -48,6 +51,31 @@ WORKLOADS = {
 HEADLINE = "bench_q10k_border"
 METRIC = "MSDA fwd+bwd throughput, 10k-query benchmark shape (fp32)"
 UNIT = "queries/s"
+
+
+def workload_string(name=None):
+    """config.workload -- the SAME string in both arms (the driver compares them)."""
+    name = name or HEADLINE
+    B, Q, H, D, pyr, K, pm, ac = WORKLOADS[name]
+    return (f"{name}: B={B} images per GPU, Q={Q} H={H} D={D} L={len(pyr)} K={K} pyramid="
+            f"{'x'.join(str(h) for h, _ in pyr)} rows, {pm}/align_corners={ac}, fp32, fwd+bwd (all 3 grads)")
+
+
+def make_inputs_device(name, seed, batch=None):
+    """Same distributions as make_inputs(), generated ON the current CUDA device (large batches: B=64 is 5 GB)."""
+    B, Q, H, D, pyr, K, pm, ac = WORKLOADS[name]
+    B = B if batch is None else batch
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    L = len(pyr)
+    npix = sum(h * w for h, w in pyr)
+    d = dict(device="cuda", generator=g)
+    t = {
+        "img": torch.randn(B, npix, H, D, **d),
+        "pts": torch.rand(B, Q, H, L, K, 2, **d),
+        "aw": torch.softmax(torch.randn(B, Q, H, L, K, **d), dim=-1),
+        "go": torch.rand(B, Q, H, D, **d),
+    }
+    return t, torch.tensor(pyr, dtype=torch.int64, device="cuda")
 
 
 def make_inputs(name, seed, device="cpu", pin=False):
@@ -201,25 +229,40 @@ def physical_gpu_index(local_index):
 # ---------------------------------------------------------------------------------------------------------------------
 # reference arm: the reference's CPU route (torch grid_sample per level) on the host cores
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_route_sample(name, reps, warm=1):
-    """Times fwd+bwd of the reference's native-torch route (port: oracle/grid_sample_port.py of frontend.py:15-68)
-    on ONE image (B=1) of the workload with all host threads; returns (queries/s, ms per image, threads, sample)."""
+def cpu_route_sample(name, reps, warm=1, budget_s=60.0):
+    """Times fwd+bwd of the reference's native-torch route (port: oracle/grid_sample_port.py of frontend.py:15-68) with
+    all host threads on the WHOLE batch of the workload (a step of the CPU arm is the same step as ours); the number of
+    repetitions is bounded by `budget_s` seconds.  One image alone (B=1, grid_sample batch N = H) is timed beside it.
+    Returns the cpu_baseline dict; value = queries/s of the whole-batch median."""
     from oracle import grid_sample_port as port
     B, Q, H, D, pyr, K, pm, ac = WORKLOADS[name]
     t, shapes = make_inputs(name, seed=0)
-    one = {k: v[:1].contiguous() for k, v in t.items()}
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    times = []
-    for i in range(warm + reps):
-        t0 = time.perf_counter()
-        port.forward_backward(one["img"], shapes, one["pts"], one["aw"], one["go"], pm, ac)
-        dt = time.perf_counter() - t0
-        if i >= warm:
-            times.append(dt)
-    times.sort()
-    med = times[len(times) // 2]
-    return Q / med, med * 1e3, torch.get_num_threads(), f"fwd+bwd of 1 of the {B} images (B=1, Q={Q}), median of {reps}"
+
+    def timed(tensors, n, w):
+        times = []
+        for i in range(w + n):
+            t0 = time.perf_counter()
+            port.forward_backward(tensors["img"], shapes, tensors["pts"], tensors["aw"], tensors["go"], pm, ac)
+            dt = time.perf_counter() - t0
+            if i >= w:
+                times.append(dt)
+            if i == 0:
+                n = max(1, min(n, int(budget_s / max(dt, 1e-3)) - w))   # bound the sample by the time budget
+            if len(times) >= n:
+                break
+        times.sort()
+        return times[len(times) // 2], len(times)
+
+    med, n = timed(t, reps, warm)
+    one = {k: v[:1].contiguous() for k, v in t.items()}
+    med1, n1 = timed(one, min(reps, 5), 1)
+    return {"value": B * Q / med, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"fwd+bwd of the whole batch (B={B}, Q={Q}), median of {n} after {warm} warm-up",
+            "ms_per_step": med * 1e3,
+            "one_image": {"value": Q / med1, "unit": UNIT, "ms": med1 * 1e3,
+                          "sample": f"fwd+bwd of 1 of the {B} images (B=1), median of {n1}"}}
 
 
 def run_reference(args):
@@ -227,16 +270,17 @@ def run_reference(args):
     if rank != 0:
         return
     B, Q, H, D, pyr, K, pm, ac = WORKLOADS[HEADLINE]
-    qps, ms_img, threads, sample = cpu_route_sample(HEADLINE, reps=max(1, args.steps), warm=max(1, args.warmup))
+    cpu = cpu_route_sample(HEADLINE, reps=max(1, args.steps), warm=max(1, args.warmup))
+    qps = cpu["value"]
     line = {
         "impl": "reference",
         "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_img * B, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": cpu["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{HEADLINE}: B={B} Q={Q} H={H} D={D} L={len(pyr)} K={K} pyramid=64^2..8^2 "
-                               f"{pm}/align_corners={ac}, fwd+bwd", "l2": "n/a (CPU)",
-                   "note": "each step = a bounded sample: 1 of the B images; ms_per_step is scaled to the full batch"},
-        "cpu_baseline": {"value": qps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": workload_string(), "l2": "n/a (CPU)",
+                   "note": "each step = fwd+bwd of the whole batch on the host cores (torch grid_sample route); the number "
+                           "of timed steps is bounded to about a minute"},
+        "cpu_baseline": cpu,
         "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -423,6 +467,292 @@ def l2_probe(K_lib):
     return res
 
 
+def shard_range(total, rank, world):
+    base, rem = divmod(total, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def time_strong_b64(rank, world, K, flush, sync, steps=5, warmup=3):
+    """BASELINE configs[4]: training fwd+bwd on the B=64 encoder shapes, batch-sharded 64/N images per rank (strong
+    scaling, no data-path collective).  Inputs are generated on the device (5 GB at N=1)."""
+    name = "train_b64_encoder_zeros"
+    B, Q, H, D, pyr, Kp, pm, ac = WORKLOADS[name]
+    lo, hi = shard_range(B, rank, world)
+    t, shapes = make_inputs_device(name, seed=100 + rank, batch=hi - lo)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+
+    def one(e=None):
+        flush.fill_(1.0)
+        if e:
+            e[0].record()
+        K.b200_multi_scale_deformable_attention_fwd(t["img"], shapes, t["pts"], t["aw"], pm, ac)
+        if e:
+            e[1].record()
+        K.b200_multi_scale_deformable_attention_bwd(t["go"], t["img"], shapes, t["pts"], t["aw"], pm, ac)
+        if e:
+            e[2].record()
+
+    for _ in range(warmup):
+        one()
+    sync()
+    for i in range(steps):
+        one(ev[i])
+    torch.cuda.synchronize()
+    sync()
+    fwd = sum(e[0].elapsed_time(e[1]) for e in ev) / steps
+    bwd = sum(e[1].elapsed_time(e[2]) for e in ev) / steps
+    del t
+    torch.cuda.empty_cache()
+    return fwd, bwd, hi - lo
+
+
+def time_query_sharded(rank, world, dist, flush, sync, steps=20, warmup=5):
+    """DETR encoder B=2 with the queries sharded over ALL ranks (they share both images): forward all-gathers the pixel
+    shards of `img`, backward reduce-scatters grad_img (msda_triton.distributed.query_sharded_msda).  The warm-up checks
+    the sharded results against the unsharded operator run on the same rank."""
+    import msda_triton
+    from msda_triton import distributed as D
+    name = "detr_encoder_zeros"
+    B, Q, H, Dh, pyr, Kp, pm, ac = WORKLOADS[name]
+    t, shapes = make_inputs(name, seed=0, device="cuda")          # the same full problem on every rank
+    npix = t["img"].shape[1]
+    res = {"workload": workload_string(name).replace("images per GPU", "images shared by all ranks"),
+           "queries_per_rank": shard_range(Q, rank, world)[1] - shard_range(Q, rank, world)[0]}
+    if world == 1:
+        a, b, c = (t[k].clone().requires_grad_(True) for k in ("img", "pts", "aw"))
+
+        def step():
+            out = msda_triton.multiscale_deformable_attention(a, shapes, b, c, pm, ac)
+            out.backward(t["go"])
+            a.grad = b.grad = c.grad = None
+        res["note"] = "N=1: the unsharded operator through the same autograd entry point, no collective"
+    else:
+        shard = D.shard_pixels(t["img"], rank, world).clone().requires_grad_(True)
+        qlo, qhi = shard_range(Q, rank, world)
+        pts = t["pts"][:, qlo:qhi].contiguous().requires_grad_(True)
+        aw = t["aw"][:, qlo:qhi].contiguous().requires_grad_(True)
+        go = t["go"][:, qlo:qhi].contiguous()
+
+        def step(keep=False):
+            out = D.query_sharded_msda(shard, npix, shapes, pts, aw, pm, ac)
+            out.backward(go)
+            g = (out.detach(), shard.grad, pts.grad, aw.grad) if keep else None
+            shard.grad = pts.grad = aw.grad = None
+            return g
+
+        # ---- equivalence (warm-up): sharded == unsharded on the same inputs ----
+        a, b, c = (t[k].clone().requires_grad_(True) for k in ("img", "pts", "aw"))
+        ref = msda_triton.multiscale_deformable_attention(a, shapes, b, c, pm, ac)
+        ref.backward(t["go"])
+        got = step(keep=True)
+        want = (ref.detach()[:, qlo:qhi], D.shard_pixels(a.grad, rank, world), b.grad[:, qlo:qhi], c.grad[:, qlo:qhi])
+        errs = torch.tensor([float((g - w).abs().max() / w.abs().max().clamp_min(1e-30)) for g, w in zip(got, want)],
+                            device="cuda", dtype=torch.float64)
+        dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+        res["sharded_vs_unsharded_max_err_over_max"] = dict(zip(("out", "grad_img_shard", "grad_points", "grad_weights"),
+                                                                 errs.tolist()))
+        res["equivalent"] = bool(errs[0] == 0 and errs[2] <= 1e-5 and errs[3] <= 1e-5 and errs[1] <= 1e-4)
+        del a, b, c, ref, got, want
+    for _ in range(warmup):
+        step()
+    sync()
+    ts = []
+    for _ in range(steps):
+        flush.fill_(1.0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    sync()
+    ts.sort()
+    ms = torch.tensor([ts[len(ts) // 2]], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    res["fwd_bwd_ms"] = float(ms)
+    if world > 1:
+        # the two collectives alone, same buffers / message sizes as inside the step
+        chunk = D.pixel_chunk(npix, world)
+        full = torch.empty(B, world * chunk, H, Dh, device="cuda")
+        sh = shard.detach()
+        outb = torch.empty_like(sh)
+        colls = {}
+        for label, fn in (("all_gather_into_tensor", lambda bb: dist.all_gather_into_tensor(full[bb], sh[bb])),
+                          ("reduce_scatter_tensor", lambda bb: dist.reduce_scatter_tensor(outb[bb], full[bb]))):
+            for _ in range(3):
+                for bb in range(B):
+                    fn(bb)
+            sync()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                for bb in range(B):
+                    fn(bb)
+            e1.record()
+            torch.cuda.synchronize()
+            m = torch.tensor([e0.elapsed_time(e1) / steps], device="cuda", dtype=torch.float64)
+            dist.all_reduce(m, op=dist.ReduceOp.MAX)
+            colls[label + "_ms"] = float(m)
+        colls["message_bytes_per_collective"] = int(full.numel() * 4)
+        colls["backend"] = "NCCL " + ".".join(str(v) for v in torch.cuda.nccl.version())
+        res["collectives"] = colls
+    return res
+
+
+def pcie_probe(h2d_bytes, d2h_bytes, dist, sync, reps=10):
+    """Pure pinned-memory copies of the e2e step's byte counts, host->device and device->host concurrently on two
+    streams, ALL RANKS AT THE SAME TIME: the host-side ceiling of `e2e` at this N (no kernels, no staging logic)."""
+    h_in = torch.empty(h2d_bytes // 4).pin_memory()
+    h_out = torch.empty(d2h_bytes // 4).pin_memory()
+    d_in = torch.empty(h2d_bytes // 4, device="cuda")
+    d_out = torch.empty(d2h_bytes // 4, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def both():
+        with torch.cuda.stream(s1):
+            d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_out, non_blocking=True)
+
+    for _ in range(3):
+        both()
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        both()
+    for st in (s1, s2):
+        torch.cuda.current_stream().wait_stream(st)
+    e1.record()
+    torch.cuda.synchronize()
+    sync()
+    ms = torch.tensor([e0.elapsed_time(e1) / reps], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms)
+
+
+def load_reference_package():
+    """The UNMODIFIED reference package staged into baseline/_ref (scripts/stage_reference.py), under the alias
+    ref_msda_triton (ours owns the name msda_triton).  None when it is not there (or Triton cannot be imported)."""
+    import importlib.util
+    pkg = ROOT / "baseline" / "_ref" / "msda_triton"
+    if not pkg.is_dir():
+        return None, "baseline/_ref not staged"
+    try:
+        if str(pkg.parent) not in sys.path:
+            sys.path.append(str(pkg.parent))   # at the END: only so that importlib.metadata finds the dist-info
+        spec = importlib.util.spec_from_file_location("ref_msda_triton", pkg / "__init__.py",
+                                                      submodule_search_locations=[str(pkg)])
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules["ref_msda_triton"] = mod
+        spec.loader.exec_module(mod)
+        from ref_msda_triton import frontend
+        return frontend, None
+    except Exception as ex:  # noqa: BLE001
+        return None, f"{type(ex).__name__}: {ex}"
+
+
+def reference_triton_gpu(flush, reps=20):
+    """BASELINE.md section 2's on-box bar: the reference's own Triton kernels, JIT-compiled for sm_100a, timed in this
+    run with the same harness (CUDA events, cold L2, public functional API, fwd under no_grad and fwd + out.backward),
+    next to ours, plus the max error of ours against them."""
+    ref, why = load_reference_package()
+    if ref is None:
+        return {"unavailable": why}
+    from msda_triton.frontend import b200_multiscale_deformable_attention as ours_fn
+    ref_fn = ref.triton_multiscale_deformable_attention
+    out = {}
+    try:
+        import triton
+        out["triton"] = triton.__version__
+    except Exception:  # noqa: BLE001
+        pass
+    for name in (HEADLINE, "detr_encoder_zeros"):
+        B, Q, H, D, pyr, Kp, pm, ac = WORKLOADS[name]
+        t, shapes = make_inputs(name, seed=0, device="cuda")
+        row = {}
+
+        def grads_of(fn):
+            a, b, c = (t[k].clone().requires_grad_(True) for k in ("img", "pts", "aw"))
+            o = fn(a, shapes, b, c, pm, ac)
+            o.backward(t["go"])
+            return [o.detach().double(), a.grad.double(), b.grad.double(), c.grad.double()]
+
+        mine, theirs = grads_of(ours_fn), grads_of(ref_fn)
+        row["ours_vs_reference_max_err_over_max"] = {
+            what: float((m - r).abs().max() / r.abs().max().clamp_min(1e-30))
+            for what, m, r in zip(("out", "grad_img", "grad_points", "grad_weights"), mine, theirs)}
+        # grad_sampling_points is piecewise constant in the cell index: the JIT-compiled Triton kernel contracts
+        # x*w - 0.5 into an FMA, the reference's written op order (and ours, and the CPU oracle) rounds twice, so a point
+        # within 1 ulp of a cell boundary lands in the neighbouring cell there -- isolated elements, counted here
+        gp_m, gp_r = mine[2], theirs[2]
+        bad = (gp_m - gp_r).abs() > 1e-4 * gp_r.abs() + 1e-5 * gp_r.abs().max()
+        row["grad_points_elements_outside_tolerance"] = {"count": int(bad.sum()), "of": int(bad.numel())}
+        del mine, theirs, gp_m, gp_r, bad
+        for who, fn in (("reference_triton", ref_fn), ("ours", ours_fn)):
+            a, b, c = (t[k].clone().requires_grad_(True) for k in ("img", "pts", "aw"))
+
+            def fwd():
+                with torch.no_grad():
+                    fn(a, shapes, b, c, pm, ac)
+
+            def fwdbwd():
+                o = fn(a, shapes, b, c, pm, ac)
+                o.backward(t["go"])
+                a.grad = b.grad = c.grad = None
+
+            for label, f in (("fwd_ms", fwd), ("fwd_bwd_ms", fwdbwd)):
+                for _ in range(5):
+                    f()
+                ts = []
+                for _ in range(reps):
+                    flush.fill_(1.0)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    f()
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ts.append(e0.elapsed_time(e1))
+                ts.sort()
+                row.setdefault(who, {})[label] = ts[len(ts) // 2]
+        row["speedup"] = {k: row["reference_triton"][k] / row["ours"][k] for k in ("fwd_ms", "fwd_bwd_ms")}
+        out[name] = row
+    out["harness"] = f"CUDA events, cold L2, 5 warm-up + {reps} reps, medians; fwd+bwd through autograd on both sides"
+    return out
+
+
+def time_deterministic(K, flush, steps=10):
+    """Backward in the deterministic (sorted-segment) mode on the headline shape, next to the atomic mode."""
+    B, Q, H, D, pyr, Kp, pm, ac = WORKLOADS[HEADLINE]
+    t, shapes = make_inputs(HEADLINE, seed=0, device="cuda")
+    out = {}
+    for label, det in (("atomic_bwd_ms", False), ("deterministic_bwd_ms", True)):
+        def f():
+            return K.b200_multi_scale_deformable_attention_bwd(t["go"], t["img"], shapes, t["pts"], t["aw"], pm, ac,
+                                                               deterministic=det)
+        for _ in range(3):
+            g = f()
+        ts = []
+        for _ in range(steps):
+            flush.fill_(1.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            f()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        out[label] = ts[len(ts) // 2]
+        if det:
+            g2 = f()
+            out["bit_reproducible"] = bool(torch.equal(g[0], g2[0]))
+    out["ratio"] = out["deterministic_bwd_ms"] / out["atomic_bwd_ms"]
+    return out
+
+
 def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -431,12 +761,16 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the MSDA path has no CPU fallback")
     torch.cuda.set_device(local)
     dist = None
+    host_group = None
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"     # keep stdout to the one JSON line (NCCL prints its banner there)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # host-side waiting (ranks 1.. idle while rank 0 times the CPU baseline): a gloo barrier blocks on a socket, an
+        # NCCL barrier would spin one host core per waiting rank
+        host_group = dist.new_group(backend="gloo")
 
     from msda_triton import _lib, kernels as K
     numa_cores = None
@@ -467,6 +801,30 @@ def run_ours(args):
     step_ms, fwd_ms, bwd_ms, e2e_ms, e2e_plain_ms = tmax.tolist()
 
     extra = {}
+    if not args.quick:
+        # ---- collective sections: every rank takes part, at every N ----
+        copy_ms = pcie_probe(h2d, d2h, dist, sync)
+        extra["pcie_probe"] = {
+            "ms_per_step_bytes": copy_ms, "h2d_gbs_per_rank": h2d / (copy_ms * 1e-3) / 1e9,
+            "d2h_gbs_per_rank": d2h / (copy_ms * 1e-3) / 1e9,
+            "aggregate_gbs_both_directions": world * (h2d + d2h) / (copy_ms * 1e-3) / 1e9,
+            "e2e_ceiling_queries_per_s": world * B * Q / (copy_ms * 1e-3),
+            "e2e_fraction_of_ceiling": copy_ms / e2e_ms,
+            "what": "the e2e step's H2D and D2H byte counts as plain pinned cudaMemcpyAsync on two streams, all ranks "
+                    "concurrently, max over ranks: the host-memory / PCIe ceiling of the e2e figure at this N"}
+        f64, b64, imgs = time_strong_b64(rank, world, K, flush, sync)
+        t64 = torch.tensor([f64, b64], device="cuda", dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t64, op=dist.ReduceOp.MAX)
+        f64, b64 = t64.tolist()
+        B64, Q64 = WORKLOADS["train_b64_encoder_zeros"][:2]
+        extra["train_b64_encoder_strong"] = {
+            "workload": "train_b64_encoder_zeros: B=64 images IN TOTAL, batch-sharded 64/N per rank, Q=22223 (DETR "
+                        "encoder pyramid), zeros/False, fp32, fwd+bwd, no collective",
+            "images_per_rank": imgs, "fwd_ms": f64, "bwd_ms": b64, "fwd_bwd_ms": f64 + b64, "scaling": "strong",
+            "queries_per_s": B64 * Q64 / ((f64 + b64) * 1e-3)}
+        extra["detr_query_sharded"] = time_query_sharded(rank, world, dist, flush, sync)
+
     cpu = None
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -487,25 +845,41 @@ def run_ours(args):
                     "gather_traffic_bytes": bm["gather"],
                     "gather_gbs": {"fwd": bm["gather"] / (fwd_ms * 1e-3) / 1e9,
                                    "bwd_read_plus_atomic": 2 * bm["gather"] / (bwd_ms * 1e-3) / 1e9}}
+        if not args.quick:
+            try:
+                extra["deterministic"] = time_deterministic(K, flush)
+            except Exception as ex:  # noqa: BLE001
+                extra["deterministic"] = {"error": str(ex)}
         if world == 1 and not args.quick:
             try:
                 extra["l2_probe"] = l2_probe(_lib.get_lib())
-                # the resource that actually binds the backward: fp32 row adds into L2 (SURVEY.md 8d "L2 gather /
-                # atomic roof", measured live with the same 8-lane x 128-bit access shape)
-                atomic_peak = extra["l2_probe"]["scatter_gbs"]
-                roofline["onchip"] = {
-                    "bound": "l2_atomic", "unit": "GB/s", "peak": atomic_peak,
-                    "peak_source": "msda_probe_scatter (red.global.add.v4.f32 over an L2-resident buffer), this run",
-                    "achieved": bm["gather"] / (bwd_ms * 1e-3) / 1e9,
-                    "frac": bm["gather"] / (bwd_ms * 1e-3) / 1e9 / atomic_peak,
-                    "note": "bytes = B*Q*H*L*K*4 corner rows of D*4 bytes added into grad_img"}
+                # roofline_time = max(compulsory / HBM peak, corner-row traffic / L2 peak); the L2 peaks
+                # are measured live by the probes (their ncu captures: profiles/r2_probe_*.csv)
+                g_peak, a_peak = extra["l2_probe"]["gather_gbs"], extra["l2_probe"]["scatter_gbs"]
+                t_hbm_b, t_l2_b = bm["bwd"] / (peak * 1e9) * 1e3, bm["gather"] / (a_peak * 1e9) * 1e3
+                t_hbm_f, t_l2_f = bm["fwd"] / (peak * 1e9) * 1e3, bm["gather"] / (g_peak * 1e9) * 1e3
+                roofline["survey_8d"] = {
+                    "definition": "roofline_time = max(compulsory_bytes / HBM_peak, corner_row_bytes / L2_peak); "
+                                  "frac = roofline_time / measured_time",
+                    "bwd": {"hbm_term_ms": t_hbm_b, "l2_atomic_term_ms": t_l2_b, "roofline_ms": max(t_hbm_b, t_l2_b),
+                            "measured_ms": bwd_ms, "frac": max(t_hbm_b, t_l2_b) / bwd_ms,
+                            "l2_peak_gbs": a_peak,
+                            "l2_peak_source": "msda_probe_scatter: red.global.add.v4.f32 of random 128-byte rows over "
+                                              "an L2-resident 32 MiB buffer, this run"},
+                    "fwd": {"hbm_term_ms": t_hbm_f, "l2_gather_term_ms": t_l2_f, "roofline_ms": max(t_hbm_f, t_l2_f),
+                            "measured_ms": fwd_ms, "frac": min(1.0, max(t_hbm_f, t_l2_f) / fwd_ms),
+                            "frac_uncapped": max(t_hbm_f, t_l2_f) / fwd_ms,
+                            "l2_peak_gbs": g_peak,
+                            "l2_peak_source": "msda_probe_gather: ld.global.nc.v4 of random 128-byte rows over an "
+                                              "L2-resident 32 MiB buffer (every row from L2), this run; the forward "
+                                              "serves 2/3 of its rows from L1, which is why it can beat this term"},
+                    "hbm_peak_gbs": peak, "hbm_peak_source": peak_src}
             except Exception as ex:  # noqa: BLE001
                 extra["l2_probe"] = {"error": str(ex)}
             for name in WORKLOADS:
-                if name == HEADLINE:
+                if name == HEADLINE or WORKLOADS[name][0] >= 32:
                     continue
-                big = WORKLOADS[name][0] >= 32
-                r = time_workload(name, 5 if big else max(5, args.steps // 4), 3, K, flush)
+                r = time_workload(name, max(5, args.steps // 4), 3, K, flush)
                 bmn = byte_model(name, r["unique_rows"])
                 extra[name] = {"fwd_ms": r["fwd_ms"], "bwd_ms": r["bwd_ms"], "fwd_bwd_ms": r["step_ms"],
                                "fwd_hbm_frac": bmn["fwd"] / (r["fwd_ms"] * 1e-3) / 1e9 / peak,
@@ -522,15 +896,17 @@ def run_ours(args):
                 extra["gdino_decoder_module_bf16"] = {"error": str(ex)}
             finally:
                 os.environ.pop("MSDA_B200_FUSED_MODULE", None)
-            qps, ms_img, threads, sample = cpu_route_sample(HEADLINE, reps=10, warm=1)
-            cpu = {"value": qps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
-                   "ms_per_image": ms_img}
+            try:
+                extra["reference_triton_gpu"] = reference_triton_gpu(flush)
+            except Exception as ex:  # noqa: BLE001
+                extra["reference_triton_gpu"] = {"unavailable": f"{type(ex).__name__}: {ex}"}
+        if not args.quick:
+            cpu = cpu_route_sample(HEADLINE, reps=10, warm=1)
         line = {
             "metric": METRIC, "value": world * B * Q / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{HEADLINE}: B={B}/GPU Q={Q} H={H} D={D} L={len(pyr)} K={Kp} pyramid=64^2..8^2 "
-                                   f"{pm}/align_corners={ac}, fwd+bwd (all 3 grads)",
+            "config": {"workload": workload_string(),
                        "l2": "flushed between steps (256 MiB overwrite outside the event pair)",
                        "parallelism": f"batch-sharded x{world}, no collective"},
             "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
@@ -542,13 +918,16 @@ def run_ours(args):
                            "step i+1 overlapped with kernels / D2H of step i",
                     "autograd_unpipelined": {"value": world * B * Q / (e2e_plain_ms * 1e-3),
                                              "ms_per_step": e2e_plain_ms}},
-            "gpu_launches": 2 * args.steps,
+            # per step: forward kernel + grad_img zero-fill (memset node) + backward kernel
+            "gpu_launches": 3 * args.steps,
+            "gpu_launches_note": "per step: msda_fwd_tiled_kernel, cudaMemsetAsync(grad_img), msda_bwd_tiled_kernel",
             "roofline": roofline,
             "cpu_baseline": cpu,
             "extra": extra,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
+        dist.barrier(group=host_group)     # ranks 1.. sleep on a socket while rank 0 runs the CPU baseline
         dist.barrier()
         dist.destroy_process_group()
 

@@ -64,41 +64,49 @@ def _backend(group) -> str:
 
 
 class _GatherPixels(torch.autograd.Function):
-    """all-gather of pixel shards along dim 1; backward = reduce-scatter (sum) of the gradient."""
+    """all-gather of pixel shards along dim 1; backward = reduce-scatter (sum) of the gradient.
+
+    Zero-copy on both sides: the gathered pyramid is laid out ``[B, world * chunk, H, D]`` (image-major, the chunks of
+    one image back to back = pixel order), so image b is ONE contiguous all-gather destination / reduce-scatter source
+    and no transposed or zero-padded staging copy of the 45 MB tensors is made (round 1 made four).  The pyramid keeps
+    its ``world * chunk - Npix`` padding rows; the kernels accept an image with more rows than the level table names."""
 
     @staticmethod
-    def forward(ctx, shard: torch.Tensor, num_pixels: int, group):
+    def forward(ctx, shard: torch.Tensor, group):
         world = dist.get_world_size(group)
-        ctx.group, ctx.world, ctx.num_pixels = group, world, num_pixels
+        ctx.group, ctx.world = group, world
         shard = shard.contiguous()
         B, chunk = shard.shape[0], shard.shape[1]
-        gathered = shard.new_empty((world,) + tuple(shard.shape))            # [g, B, chunk, H, D]
-        dist.all_gather_into_tensor(gathered.view(world * B, *shard.shape[1:]), shard, group=group)
-        full = gathered.transpose(0, 1).reshape(B, world * chunk, *shard.shape[2:])
-        return full[:, :num_pixels].contiguous()
+        full = shard.new_empty((B, world * chunk) + tuple(shard.shape[2:]))
+        for b in range(B):
+            dist.all_gather_into_tensor(full[b], shard[b], group=group)
+        return full
 
     @staticmethod
     def backward(ctx, grad_full: torch.Tensor):
         world, group = ctx.world, ctx.group
-        B, npix = grad_full.shape[0], grad_full.shape[1]
-        chunk = pixel_chunk(npix, world)
-        padded = grad_full.new_zeros((B, world * chunk) + tuple(grad_full.shape[2:]))
-        padded[:, :npix] = grad_full
-        # [B, g, chunk, ...] -> [g, B, chunk, ...]: rank r receives the sum of everyone's slice r
-        send = padded.view(B, world, chunk, *grad_full.shape[2:]).transpose(0, 1).contiguous()
-        out = send.new_empty(send.shape[1:])
+        grad_full = grad_full.contiguous()
+        B, chunk = grad_full.shape[0], grad_full.shape[1] // world
+        out = grad_full.new_empty((B, chunk) + tuple(grad_full.shape[2:]))
         if _backend(group) == "gloo":
-            dist.all_reduce(send, group=group)                                # gloo has no reduce_scatter
-            out.copy_(send[dist.get_rank(group)])
+            dist.all_reduce(grad_full, group=group)                           # gloo has no reduce_scatter
+            r = dist.get_rank(group)
+            out.copy_(grad_full[:, r * chunk:(r + 1) * chunk])
         else:
-            dist.reduce_scatter_tensor(out, send.view(world * B, *send.shape[2:]), op=dist.ReduceOp.SUM, group=group)
-        return out, None, None
+            for b in range(B):
+                dist.reduce_scatter_tensor(out[b], grad_full[b], op=dist.ReduceOp.SUM, group=group)
+        return out, None
 
 
-def gather_pixels(img_shard: torch.Tensor, num_pixels: int, group=None) -> torch.Tensor:
-    """[B, chunk, H, D] pixel shards -> the full pyramid [B, Npix, H, D] on every rank of `group` (differentiable:
-    the backward pass reduce-scatters grad_img over NVLink, message = B*Npix*H*D*elem_size bytes)."""
-    return _GatherPixels.apply(img_shard, num_pixels, group)
+def gather_pixels(img_shard: torch.Tensor, num_pixels: int, group=None, keep_padding: bool = False) -> torch.Tensor:
+    """[B, chunk, H, D] pixel shards -> the full pyramid on every rank of `group` (differentiable: the backward pass
+    reduce-scatters grad_img over NVLink, message = B * world * chunk * H * D * elem_size bytes).
+
+    keep_padding=False: ``[B, Npix, H, D]`` (a view of the padded buffer when world * chunk > Npix).
+    keep_padding=True : ``[B, world * chunk, H, D]`` contiguous -- what :func:`query_sharded_msda` hands to the CUDA
+    kernels so that nothing is copied."""
+    full = _GatherPixels.apply(img_shard, group)
+    return full if keep_padding else full[:, :num_pixels]
 
 
 def query_sharded_msda(
@@ -116,7 +124,10 @@ def query_sharded_msda(
     forward : all-gather(img shards) -> local queries sample the full pyramid        (no other collective)
     backward: local partial grad_img -> reduce-scatter(sum) back to pixel shards     (the only backward collective)
     """
-    img_full = gather_pixels(img_shard, num_pixels, group)
+    on_gpu = img_shard.is_cuda
+    # CUDA: the kernels read the padded gather buffer in place and the backward writes grad_img straight into the
+    # reduce-scatter source; the torch route (CPU tensors) splits the pyramid by level sizes and gets the exact view
+    img_full = gather_pixels(img_shard, num_pixels, group, keep_padding=on_gpu)
     return multiscale_deformable_attention(
         img_full, img_shapes, sampling_points_local, attention_weights_local, padding_mode, align_corners)
 

@@ -22,17 +22,17 @@ def grid_sample_msda(img, img_shapes, sampling_points, attention_weights, paddin
     hw = [(int(h), int(w)) for h, w in img_shapes.tolist()]
     grid_all = sampling_points * 2 - 1                                   # [0,1] -> [-1,1]
     start = 0
-    out = None
+    samples = []
     for lvl, (h, w) in enumerate(hw):
         feat = img[:, start:start + h * w]                               # [B, h*w, H, D]
         start += h * w
         feat = feat.permute(0, 2, 3, 1).reshape(B * H, D, h, w)          # NCHW with N = B*H
         grid = grid_all[:, :, :, lvl].permute(0, 2, 1, 3, 4).reshape(B * H, Q, K, 2)
         smp = F.grid_sample(feat, grid, mode="bilinear", padding_mode=padding_mode, align_corners=align_corners)
-        smp = smp.reshape(B, H, D, Q, K).permute(0, 3, 1, 4, 2)          # [B, Q, H, K, D]
-        part = (attention_weights[:, :, :, lvl, :, None] * smp).sum(dim=3)
-        out = part if out is None else out + part
-    return out
+        samples.append(smp.reshape(B, H, D, Q, K).permute(0, 3, 1, 4, 2))   # [B, Q, H, K, D]
+    # as the reference: materialise [B, Q, H, L, K, D], weight, and reduce over (level, point) in one sum
+    stacked = torch.stack(samples, dim=3)
+    return (attention_weights[..., None] * stacked).sum(dim=(3, 4))
 
 
 def forward_backward(img, img_shapes, sampling_points, attention_weights, out_grad, padding_mode, align_corners):
