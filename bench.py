@@ -750,6 +750,31 @@ def time_deterministic(K, flush, steps=10):
             g2 = f()
             out["bit_reproducible"] = bool(torch.equal(g[0], g2[0]))
     out["ratio"] = out["deterministic_bwd_ms"] / out["atomic_bwd_ms"]
+    out["how"] = "exact (quantised) fp32 row adds, csrc/msda_bwd_detq.cu: amax + row-bound pre-passes, then the tuned backward"
+    # the sorted-segment path (radix sort + ordered segment sums; full fp32 accuracy for any input) for comparison
+    from msda_triton import _lib
+    os.environ["MSDA_B200_DET_VARIANT"] = "0"
+    _lib.reload_tuning()
+    try:
+        def f0():
+            return K.b200_multi_scale_deformable_attention_bwd(t["go"], t["img"], shapes, t["pts"], t["aw"], pm, ac,
+                                                               deterministic=True)
+        for _ in range(2):
+            f0()
+        ts = []
+        for _ in range(5):
+            flush.fill_(1.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            f0()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        out["sorted_segment_bwd_ms"] = ts[len(ts) // 2]
+    finally:
+        os.environ.pop("MSDA_B200_DET_VARIANT", None)
+        _lib.reload_tuning()
     return out
 
 

@@ -176,6 +176,9 @@ size_t msda_backward_workspace_bytes(const msda_problem *prob, int flags) {
         if (prob->Q == 0) return 0;
         msda::KernelArgs a;
         fill_args(a, prob, 1);
+        // fp32 tuned shapes: exact (quantised) row adds need a few MB; everything else sorts (24 B per corner)
+        if (!force_generic() && msda::tuning().det_variant != 0 && msda::quant_backward_supported(a, prob->dtype))
+            return msda::detq_workspace_bytes(a);
         return msda::det_supported(a) ? msda::det_workspace_bytes(a) : 0;
     }
     if (prob->dtype == MSDA_DTYPE_F16 || prob->dtype == MSDA_DTYPE_BF16)
@@ -201,6 +204,35 @@ int msda_backward(void *grad_img, void *grad_points, void *grad_weights, const v
     rc = device_info(&dev);
     if (rc != MSDA_OK) return rc;
 
+    if ((flags & MSDA_BWD_DETERMINISTIC) && need_img && img_elems > 0 && !no_units && !force_generic() &&
+        msda::tuning().det_variant != 0) {
+        // fp32 tuned shapes: ONE pass of the tuned backward with exact (quantised) row adds, msda_bwd_detq.cu
+        msda::KernelArgs q;
+        fill_args(q, prob, 4);
+        if (msda::quant_backward_supported(q, prob->dtype) && grad_out && img && img_shapes && sampling_points &&
+            attention_weights && aligned(img, 16) && aligned(grad_out, 16) && aligned(grad_img, 16) &&
+            aligned(sampling_points, 16) && aligned(attention_weights, 8) && aligned(img_shapes, 8) &&
+            (!need_pts || aligned(grad_points, 16)) && (!need_aw || aligned(grad_weights, 8))) {
+            const size_t want = msda::detq_workspace_bytes(q);
+            if (!workspace || workspace_bytes < want || !aligned(workspace, 256))
+                return fail(MSDA_ERR_WORKSPACE, "msda_backward: deterministic mode needs a 256-byte aligned workspace of "
+                                                "%zu bytes, got %zu", want, workspace_bytes);
+            cudaError_t e0 = cudaMemsetAsync(grad_img, 0, img_elems * es, st);
+            if (e0 != cudaSuccess) return fail_cuda(e0, "msda_backward zero-fill");
+            q.img = img;
+            q.shapes = reinterpret_cast<const long long *>(img_shapes);
+            q.pts = sampling_points;
+            q.aw = attention_weights;
+            q.gout = grad_out;
+            q.gimg = grad_img;
+            q.gpts = grad_points;
+            q.gaw = grad_weights;
+            q.flags = flags & MSDA_BWD_NEED_ALL;
+            e0 = msda::launch_backward_detq(q, prob->dtype, workspace, dev.sm_count, st);
+            if (e0 == cudaSuccess) return MSDA_OK;
+            if (e0 != cudaErrorNotSupported) return fail_cuda(e0, "msda_backward deterministic (exact row adds) path");
+        }
+    }
     if ((flags & MSDA_BWD_DETERMINISTIC) && need_img) {
         // grad_points / grad_weights from the regular kernel (no atomics there), grad_img by sorted segments
         if (need_pts || need_aw) {

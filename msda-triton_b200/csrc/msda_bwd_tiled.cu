@@ -39,8 +39,11 @@ template <int VEC, int LANES> __device__ __forceinline__ void red_add_row(float 
 // PADDED: see the forward kernel -- a.LK <= LK real points, per-point loads / stores; dead slots are gathered (point
 // (0,0), weight 0) but add nothing.
 // SPLIT: units with more than LK points run as `subs` sub-units of LK slots each (decode_tile in msda_tiled.cuh).
+// QUANT: deterministic mode (msda_bwd_detq.cu).  Every value added to grad_img is first rounded to a multiple of a
+// power-of-two quantum q chosen per (b, h, level) such that NO partial sum of a row can exceed 2^24 q: all the fp32 adds
+// of the row are then exact, hence associative, and the relaxed atomics give the same bits in any order.
 template <typename T, int LANES, int LK, bool BORDER, int NB, int THREADS, bool FUSED, int VEC, bool PADDED,
-          bool SPLIT>
+          bool SPLIT, bool QUANT = false>
 __global__ void __launch_bounds__(THREADS, 1)
     msda_bwd_tiled_kernel(const KernelArgs a, const WaveSchedule ws, const int subs_arg) {
     using Cfg = TiledCfg<T, LANES, LK>;
@@ -102,12 +105,15 @@ __global__ void __launch_bounds__(THREADS, 1)
 
         TileTap tap[PPL];
         float sx[PPL], sy[PPL];
+        float quantum[QUANT ? PPL : 1];   // QUANT: quantum of the level of this lane's points (0 = leave unquantised)
 #pragma unroll
         for (int pp = 0; pp < PPL; ++pp) {
-            const Level lv = s_lv[slot_level(p0 + j * PPL + pp, a)];
+            const int lvl = slot_level(p0 + j * PPL + pp, a);
+            const Level lv = s_lv[lvl];
             tap[pp] = resolve_tap<BORDER>(op.xy[2 * pp], op.xy[2 * pp + 1], lv, align, row_bytes);
             sx[pp] = align ? (float)(lv.w - 1) : (float)lv.w;
             sy[pp] = align ? (float)(lv.h - 1) : (float)lv.h;
+            if constexpr (QUANT) quantum[pp] = row_quantum(a, (tile / tiles_per_bh) * a.L + lvl);
         }
 
         // part[(jj*PPL + pp)*3 + {0,1,2}] : point jj*PPL+pp  ->  {grad weight, d/dx, d/dy} partial over my channels
@@ -119,6 +125,7 @@ __global__ void __launch_bounds__(THREADS, 1)
             for (int jj0 = 0; jj0 < LANES; jj0 += NB) {
                 Raw raw[NB][4];
                 float fx[NB], fy[NB], fw[NB];
+                float fq[QUANT ? NB : 1];
                 unsigned o[NB][4];
                 unsigned msk[NB];
 #pragma unroll
@@ -132,6 +139,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                     fx[n] = __shfl_sync(0xffffffffu, tap[pp].dx, src, LANES);
                     fy[n] = __shfl_sync(0xffffffffu, tap[pp].dy, src, LANES);
                     fw[n] = __shfl_sync(0xffffffffu, op.wa[pp], src, LANES);
+                    if constexpr (QUANT) fq[n] = __shfl_sync(0xffffffffu, quantum[pp], src, LANES);
                     corner_offsets(off, pack, row_bytes, o[n]);
                     msk[n] = BORDER ? 0xFu : ((pack >> kPackMaskShift) & 0xFu);
                     // always in range (clamped rows); zeros padding is applied to the dot products below
@@ -159,8 +167,23 @@ __global__ void __launch_bounds__(THREADS, 1)
                         if (need_img) {
                             const float s = fw[n] * bw[c];
                             float gv[VEC];
+                            if constexpr (!QUANT) {
 #pragma unroll
-                            for (int e = 0; e < VEC; ++e) gv[e] = go[e] * s;
+                                for (int e = 0; e < VEC; ++e) gv[e] = go[e] * s;
+                            } else {
+                                // |go * s| < 2^24 q, so |go * s| + 1.5 * 2^23 q lies in [1.5, 3.5) * 2^23 q, where fp32 has a spacing
+                                // of q (or 2q):
+                                // the FMA rounds the exact product to a multiple of q, the subtraction is exact, the sign
+                                // goes back on with one logic op.  fq == 0 (nothing to quantise against): plain product.
+                                const float magic = fq[n] * 12582912.0f;   // 1.5 * 2^23
+                                const unsigned s_sign = __float_as_uint(s) & 0x80000000u;
+#pragma unroll
+                                for (int e = 0; e < VEC; ++e) {
+                                    const float mag = fmaf(fabsf(go[e]), fabsf(s), magic) - magic;
+                                    gv[e] = __uint_as_float(__float_as_uint(mag) |
+                                                            ((__float_as_uint(go[e]) & 0x80000000u) ^ s_sign));
+                                }
+                            }
                             float *dst = reinterpret_cast<float *>(gimg_base + (size_t)o[n][c] * kAccScale);
                             if (live && alive && (BORDER || ((msk[n] >> c) & 1u))) red_add_row<VEC, LANES>(dst, gv);
                         }
@@ -292,7 +315,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 
 
 template <typename T, int LANES, int LK, bool FUSED = false, int VEC = 16 / (int)sizeof(T), bool PADDED = false,
-          bool SPLIT = false>
+          bool SPLIT = false, bool QUANT = false>
 static cudaError_t launch_tiled_t(const KernelArgs &a, int sm_count, cudaStream_t st, int subs = 1) {
     constexpr int THREADS = 512, NB = 2;
     constexpr int G = TiledCfg<T, LANES, LK>::G;
@@ -314,10 +337,10 @@ static cudaError_t launch_tiled_t(const KernelArgs &a, int sm_count, cudaStream_
         if (e != cudaSuccess) return e;
     }
     if (a.border)
-        msda_bwd_tiled_kernel<T, LANES, LK, true, NB, THREADS, FUSED, VEC, PADDED, SPLIT>
+        msda_bwd_tiled_kernel<T, LANES, LK, true, NB, THREADS, FUSED, VEC, PADDED, SPLIT, QUANT>
             <<<grid, THREADS, 0, st>>>(a, ws, subs);
     else
-        msda_bwd_tiled_kernel<T, LANES, LK, false, NB, THREADS, FUSED, VEC, PADDED, SPLIT>
+        msda_bwd_tiled_kernel<T, LANES, LK, false, NB, THREADS, FUSED, VEC, PADDED, SPLIT, QUANT>
             <<<grid, THREADS, 0, st>>>(a, ws, subs);
     return cudaGetLastError();
 }
@@ -374,6 +397,15 @@ static bool tmem_backward_wanted(const KernelArgs &a, int sm_count) {
     (void)sm_count;
     if (!(a.flags & kNeedImg)) return false;
     return tuning().bwd_tmem > 0;
+}
+
+// Deterministic mode, exact row adds (msda_bwd_detq.cu prepared a.q_slmax / a.q_amax): fp32, D == 32, L*K == 16.
+bool quant_backward_supported(const KernelArgs &a, int dtype) {
+    return dtype == 0 && a.D == 32 && a.LK == 16 && a.L <= 8 && tiled_offsets_fit(a, sizeof(float));
+}
+cudaError_t launch_backward_tiled_quant(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st) {
+    if (!quant_backward_supported(a, dtype)) return cudaErrorNotSupported;
+    return launch_tiled_t<float, 8, 16, false, 4, false, false, true>(a, sm_count, st);
 }
 
 cudaError_t launch_backward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st) {

@@ -33,6 +33,10 @@ struct KernelArgs {
     void *gproj;               // bwd: [B, Q, H, L, K, 3]
     float *gref;               // bwd: [B, Q, ref_dim] fp32, zero-filled by the library, accumulated with atomics
     int ref_dim;
+    // deterministic backward by exact (quantised) row adds, msda_bwd_detq.cu: per (b, h, level) the largest row bound
+    // in units of amax / 4096, and {max |grad_out|, max |attention weight|} as float bits
+    const unsigned long long *q_slmax;
+    const unsigned *q_amax;
     long long units;           // B*Q*H  (one unit = one output row (b,q,h))
     int B, Q, H, D, L, K, Npix;
     int LK;                    // L*K

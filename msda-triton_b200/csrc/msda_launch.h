@@ -24,6 +24,13 @@ cudaError_t launch_module_backward_tiled(const KernelArgs &a, int dtype, int sm_
 // fp32, D == 32, L*K == 16, K == 4, grad_img requested.  cudaErrorNotSupported otherwise.
 cudaError_t launch_backward_tmem(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st);
 
+// Deterministic mode by exact (quantised) row adds: msda_bwd_detq.cu prepares the quanta in `workspace`, then runs the
+// tuned backward (all requested gradients in one pass).  cudaErrorNotSupported outside fp32, D == 32, L*K == 16.
+bool quant_backward_supported(const KernelArgs &a, int dtype);
+size_t detq_workspace_bytes(const KernelArgs &a);
+cudaError_t launch_backward_detq(const KernelArgs &a, int dtype, void *workspace, int sm_count, cudaStream_t st);
+cudaError_t launch_backward_tiled_quant(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st);
+
 // grad_img alone, without gathers (split backward; msda_bwd_scatter.cu).  a.gimg = zero-filled fp32 accumulation image.
 cudaError_t launch_backward_scatter(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st);
 
