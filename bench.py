@@ -554,24 +554,60 @@ def time_query_sharded(rank, world, dist, flush, sync, steps=20, warmup=5):
                                                                  errs.tolist()))
         res["equivalent"] = bool(errs[0] == 0 and errs[2] <= 1e-5 and errs[3] <= 1e-5 and errs[1] <= 1e-4)
         del a, b, c, ref, got, want
-    for _ in range(warmup):
-        step()
-    sync()
-    ts = []
-    for _ in range(steps):
-        flush.fill_(1.0)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        step()
-        e1.record()
-        torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
-    sync()
-    ts.sort()
-    ms = torch.tensor([ts[len(ts) // 2]], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    res["fwd_bwd_ms"] = float(ms)
+    def timed(fn):
+        for _ in range(warmup):
+            fn()
+        sync()
+        ts = []
+        for _ in range(steps):
+            flush.fill_(1.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        sync()
+        ts.sort()
+        ms = torch.tensor([ts[len(ts) // 2]], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    if world == 1:
+        res["fwd_bwd_ms"] = timed(step)
+    else:
+        res["nccl"] = {"fwd_bwd_ms": timed(step),
+                       "how": "all_gather_into_tensor / reduce_scatter_tensor per image, zero-copy (distributed.query_sharded_msda)"}
+        # ---- the same step over NVLink peer memory: the library's own all-gather / reduce-scatter kernels ----
+        try:
+            ex = D.PeerPixelExchange(B, npix, H, Dh)
+
+            def peer_step(keep=False):
+                out = D.peer_query_sharded_msda(ex, shard, shapes, pts, aw, pm, ac)
+                out.backward(go)
+                g = (out.detach(), shard.grad, pts.grad, aw.grad) if keep else None
+                shard.grad = pts.grad = aw.grad = None
+                return g
+
+            got = peer_step(keep=True)
+            base = step(keep=True)
+            errs = torch.tensor([float((g - w).abs().max() / w.abs().max().clamp_min(1e-30)) for g, w in zip(got, base)],
+                                device="cuda", dtype=torch.float64)
+            dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+            res["peer_memory"] = {
+                "fwd_bwd_ms": timed(peer_step),
+                "vs_nccl_route_max_err_over_max": dict(zip(("out", "grad_img_shard", "grad_points", "grad_weights"),
+                                                           errs.tolist())),
+                "how": "msda_peer_all_gather / msda_peer_reduce_scatter (csrc/msda_peer.cu): P2P loads over NVLink from "
+                       "symmetric memory, one launch per collective, the backward accumulates in the buffer the peers read"}
+            sh_det = shard.detach()
+            res["peer_memory"]["all_gather_ms"] = timed(lambda: ex.all_gather(sh_det))
+            res["peer_memory"]["reduce_scatter_ms"] = timed(lambda: ex.reduce_scatter())
+            res["fwd_bwd_ms"] = min(res["nccl"]["fwd_bwd_ms"], res["peer_memory"]["fwd_bwd_ms"])
+        except Exception as ex_:  # noqa: BLE001
+            res["peer_memory"] = {"unavailable": f"{type(ex_).__name__}: {ex_}"}
+            res["fwd_bwd_ms"] = res["nccl"]["fwd_bwd_ms"]
     if world > 1:
         # the two collectives alone, same buffers / message sizes as inside the step
         chunk = D.pixel_chunk(npix, world)

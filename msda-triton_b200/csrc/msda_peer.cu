@@ -1,0 +1,205 @@
+// msda_peer.cu -- query-sharded MSDA over NVLink peer memory: the pixel-shard all-gather in front of the forward and the
+// grad_img reduce-scatter behind the backward as ONE kernel each, reading the peers' buffers directly (P2P loads over
+// NVLink / NVSwitch) instead of going through NCCL.
+//
+// Setting (the reference has no distributed code): the ranks of a group share images.  Every rank holds a
+// pixel shard of `img` and a query shard of the sampling points; forward needs the full pyramid on every rank, backward
+// produces a full-size PARTIAL grad_img on every rank whose sum has to end up pixel-sharded again
+// (/root/reference/src/msda_triton/kernels.py:549-553 is the only coupling between output rows).
+//
+// All buffers the peers read live in symmetric memory (the host side allocates them with torch symmetric memory and
+// hands over the peers' device pointers).  Cross-rank ordering uses four flag rows per rank,
+//      flags[slot][src]   slot in {AG_READY, AG_DONE, RS_READY, RS_DONE},   written ONLY by rank `src`,
+// that carry monotonically increasing epochs (call counters kept by the host wrapper), so nothing is ever reset:
+//   all-gather e:   wait AG_DONE >= e-1 (peers finished reading my staging shard) and RS_DONE >= r (peers finished
+//                   reading my partial grad_img of the previous backward -- the coming backward overwrites it)
+//                   -> copy my shard into the staging buffer -> signal AG_READY = e -> wait for everybody's AG_READY
+//                   -> pull the world-1 remote shards (own shard: local copy) -> signal AG_DONE = e
+//   reduce-scatter: signal RS_READY = r (stream order: my backward has completed) -> wait for everybody's RS_READY
+//                   -> out[b, i] = sum over ranks (fixed order 0..world-1: deterministic given the partials) of
+//                   partial_rank[b, my_rank * chunk + i] -> signal RS_DONE = r
+// The kernels are persistent-sized (one CTA per SM): CTAs spin on the flags, so the whole grid has to be resident.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "msda_b200.h"
+
+namespace {
+
+constexpr int kThreads = 512;
+enum { AG_READY = 0, AG_DONE = 1, RS_READY = 2, RS_DONE = 3 };
+constexpr int kMaxWorld = 16;
+
+struct PeerArgs {
+    const uint4 *shards[kMaxWorld];       // every rank's staging shard   [B, chunk, H, D]
+    const float4 *partials[kMaxWorld];    // every rank's partial grad_img [B, world * chunk, H, D] fp32
+    uint32_t *flags[kMaxWorld];           // every rank's flag block [4][world]
+    uint32_t *counters;                   // local, 4 words, zero between kernels
+    int world, rank;
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint4 ld_remote(const uint4 *p) {   // no L1 allocation: the line belongs to another GPU
+    uint4 v;
+    asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+// thread 0 of the CTA: wait until every rank's entry of `slot` in MY flag block has reached `epoch`
+__device__ void wait_all(const PeerArgs &a, int slot, uint32_t epoch) {
+    if (threadIdx.x == 0) {
+        const uint32_t *mine = a.flags[a.rank] + slot * a.world;
+        for (int s = 0; s < a.world; ++s)
+            while ((int32_t)(ld_acquire_sys(mine + s) - epoch) < 0) __nanosleep(64);
+    }
+    __syncthreads();
+}
+// every CTA calls this after its part of the preceding phase; the last one to arrive publishes `epoch` in `slot` of
+// every rank's flag block (entry [slot][my rank])
+__device__ void arrive_and_signal(const PeerArgs &a, int counter, int slot, uint32_t epoch) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        if (atomicAdd(a.counters + counter, 1u) == gridDim.x - 1) {
+            a.counters[counter] = 0u;
+            __threadfence_system();
+            for (int p = 0; p < a.world; ++p) st_release_sys(a.flags[p] + slot * a.world + a.rank, epoch);
+        }
+    }
+}
+
+// n16: uint4 per image and rank (chunk * H * D * elem_size / 16)
+__global__ void __launch_bounds__(kThreads) peer_all_gather_kernel(const PeerArgs a, uint4 *__restrict__ full,
+                                                                   const uint4 *__restrict__ shard_user,
+                                                                   uint4 *__restrict__ staging, const long long B,
+                                                                   const long long n16, const uint32_t epoch_ag,
+                                                                   const uint32_t epoch_rs_done) {
+    const long long tid = (long long)blockIdx.x * kThreads + threadIdx.x, stride = (long long)gridDim.x * kThreads;
+    wait_all(a, AG_DONE, epoch_ag - 1u);
+    wait_all(a, RS_DONE, epoch_rs_done);
+    for (long long i = tid; i < B * n16; i += stride) {
+        const uint4 v = __ldg(shard_user + i);
+        staging[i] = v;
+        const long long b = i / n16, k = i - b * n16;
+        full[(b * a.world + a.rank) * n16 + k] = v;          // my own part of the pyramid
+    }
+    arrive_and_signal(a, 0, AG_READY, epoch_ag);
+    wait_all(a, AG_READY, epoch_ag);
+    // remote parts: peer p's shard of image b -> rows [p * chunk, (p+1) * chunk) of image b.  Peers are visited starting
+    // with my right-hand neighbour so that at any moment the ranks read from different peers.
+    const long long per_peer = B * n16;
+    for (int d = 1; d < a.world; ++d) {
+        const int p = (a.rank + d) % a.world;
+        const uint4 *__restrict__ src = a.shards[p];
+        long long i = tid;
+        for (; i + 3 * stride < per_peer; i += 4 * stride) {   // four loads in flight per thread
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = ld_remote(src + i + u * stride);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long j = i + u * stride, b = j / n16, k = j - b * n16;
+                full[(b * a.world + p) * n16 + k] = v[u];
+            }
+        }
+        for (; i < per_peer; i += stride) {
+            const long long b = i / n16, k = i - b * n16;
+            full[(b * a.world + p) * n16 + k] = ld_remote(src + i);
+        }
+    }
+    arrive_and_signal(a, 1, AG_DONE, epoch_ag);
+}
+
+// n4: float4 per image and rank
+__global__ void __launch_bounds__(kThreads) peer_reduce_scatter_kernel(const PeerArgs a, float4 *__restrict__ out,
+                                                                       const long long B, const long long n4,
+                                                                       const uint32_t epoch_rs) {
+    const long long tid = (long long)blockIdx.x * kThreads + threadIdx.x, stride = (long long)gridDim.x * kThreads;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {    // stream order: the backward that filled my partial has completed
+        __threadfence_system();
+        for (int p = 0; p < a.world; ++p) st_release_sys(a.flags[p] + RS_READY * a.world + a.rank, epoch_rs);
+    }
+    wait_all(a, RS_READY, epoch_rs);
+    for (long long i = tid; i < B * n4; i += stride) {
+        const long long b = i / n4, k = i - b * n4;
+        const long long off = (b * a.world + a.rank) * n4 + k;   // my pixel chunk inside every rank's partial image
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint4 v[kMaxWorld];
+#pragma unroll
+        for (int r = 0; r < kMaxWorld; ++r)
+            if (r < a.world) v[r] = ld_remote(reinterpret_cast<const uint4 *>(a.partials[r] + off));
+#pragma unroll
+        for (int r = 0; r < kMaxWorld; ++r)
+            if (r < a.world) {
+                acc.x += __uint_as_float(v[r].x);
+                acc.y += __uint_as_float(v[r].y);
+                acc.z += __uint_as_float(v[r].z);
+                acc.w += __uint_as_float(v[r].w);
+            }
+        out[i] = acc;
+    }
+    arrive_and_signal(a, 2, RS_DONE, epoch_rs);
+}
+
+int fill(PeerArgs &k, const msda_peer_ctx *ctx) {
+    if (!ctx || ctx->world < 1 || ctx->world > kMaxWorld || ctx->rank < 0 || ctx->rank >= ctx->world) return -1;
+    if (!ctx->peer_shards || !ctx->peer_partials || !ctx->peer_flags || !ctx->counters) return -1;
+    k.world = ctx->world;
+    k.rank = ctx->rank;
+    k.counters = ctx->counters;
+    for (int r = 0; r < ctx->world; ++r) {
+        k.shards[r] = static_cast<const uint4 *>(ctx->peer_shards[r]);
+        k.partials[r] = static_cast<const float4 *>(ctx->peer_partials[r]);
+        k.flags[r] = ctx->peer_flags[r];
+        if (!k.shards[r] || !k.partials[r] || !k.flags[r]) return -1;
+    }
+    return 0;
+}
+
+int sm_count_of_current_device() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    return n;
+}
+
+}  // namespace
+
+extern "C" {
+
+int msda_peer_all_gather(void *full, const void *shard, const msda_peer_ctx *ctx, int64_t B, int64_t shard_bytes_per_image,
+                         uint32_t epoch_all_gather, uint32_t epoch_reduce_scatter_done, void *stream) {
+    PeerArgs k;
+    if (fill(k, ctx) != 0 || !full || !shard || B < 0 || shard_bytes_per_image < 0 || shard_bytes_per_image % 16 != 0)
+        return MSDA_ERR_BAD_SHAPE;
+    if (((uintptr_t)full | (uintptr_t)shard) & 15u) return MSDA_ERR_BAD_SHAPE;
+    const int sms = sm_count_of_current_device();
+    if (sms <= 0) return (int)cudaErrorInvalidDevice;
+    uint4 *staging = const_cast<uint4 *>(k.shards[k.rank]);
+    peer_all_gather_kernel<<<sms, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        k, static_cast<uint4 *>(full), static_cast<const uint4 *>(shard), staging, (long long)B,
+        (long long)(shard_bytes_per_image / 16), epoch_all_gather, epoch_reduce_scatter_done);
+    return (int)cudaGetLastError();
+}
+
+int msda_peer_reduce_scatter(void *grad_shard, const msda_peer_ctx *ctx, int64_t B, int64_t shard_floats_per_image,
+                             uint32_t epoch_reduce_scatter, void *stream) {
+    PeerArgs k;
+    if (fill(k, ctx) != 0 || !grad_shard || B < 0 || shard_floats_per_image < 0 || shard_floats_per_image % 4 != 0)
+        return MSDA_ERR_BAD_SHAPE;
+    if ((uintptr_t)grad_shard & 15u) return MSDA_ERR_BAD_SHAPE;
+    const int sms = sm_count_of_current_device();
+    if (sms <= 0) return (int)cudaErrorInvalidDevice;
+    peer_reduce_scatter_kernel<<<sms, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        k, static_cast<float4 *>(grad_shard), (long long)B, (long long)(shard_floats_per_image / 4), epoch_reduce_scatter);
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"

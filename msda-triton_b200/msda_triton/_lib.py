@@ -19,6 +19,13 @@ PAD_ZEROS, PAD_BORDER = 0, 1
 BWD_NEED_IMG, BWD_NEED_POINTS, BWD_NEED_WEIGHTS, BWD_DETERMINISTIC, BWD_NEED_REF = 1, 2, 4, 8, 16
 
 
+class MsdaPeerCtx(ctypes.Structure):
+    """struct msda_peer_ctx (include/msda_b200.h): every rank's device pointers, as host arrays."""
+    _fields_ = [("world", ctypes.c_int32), ("rank", ctypes.c_int32),
+                ("peer_shards", ctypes.POINTER(ctypes.c_void_p)), ("peer_partials", ctypes.POINTER(ctypes.c_void_p)),
+                ("peer_flags", ctypes.POINTER(ctypes.c_void_p)), ("counters", ctypes.c_void_p)]
+
+
 class MsdaProblem(ctypes.Structure):
     """struct msda_problem (include/msda_b200.h)."""
     _fields_ = [(n, ctypes.c_int64) for n in ("B", "Npix", "H", "D", "Q", "L", "K")] + [
@@ -58,6 +65,10 @@ def _load() -> ctypes.CDLL:
     lib.msda_module_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ci, pp, ci, vp, sz, vp]
     lib.msda_level_table.restype = ci
     lib.msda_level_table.argtypes = [vp, vp, i64, i64, vp]
+    lib.msda_peer_all_gather.restype = ci
+    lib.msda_peer_all_gather.argtypes = [vp, vp, ctypes.POINTER(MsdaPeerCtx), i64, i64, ctypes.c_uint32, ctypes.c_uint32, vp]
+    lib.msda_peer_reduce_scatter.restype = ci
+    lib.msda_peer_reduce_scatter.argtypes = [vp, ctypes.POINTER(MsdaPeerCtx), i64, i64, ctypes.c_uint32, vp]
     lib.msda_probe_gather.restype = ci
     lib.msda_probe_gather.argtypes = [vp, vp, i64, i64, ctypes.c_uint32, vp]
     lib.msda_probe_scatter.restype = ci

@@ -11,16 +11,22 @@ couples rows of the same image (``/root/reference/src/msda_triton/kernels.py:16-
   pixel shards (:func:`gather_pixels`), backward is the exact transpose: ONE reduce-scatter (sum) of ``grad_img``.
   ``grad_sampling_points`` / ``grad_attention_weights`` are query-local and need nothing.
 
-All collectives go through ``torch.distributed`` (NCCL on GPUs; the same code runs on gloo for CPU tests, where
-``reduce_scatter`` is emulated with ``all_reduce`` + slice because gloo lacks it).
+The NCCL route goes through ``torch.distributed`` (the same code runs on gloo for CPU tests, where ``reduce_scatter``
+is emulated with ``all_reduce`` + slice because gloo lacks it).  On one NVLink domain :class:`PeerPixelExchange` replaces
+both collectives with the library's own kernels over peer memory (``csrc/msda_peer.cu``): the all-gather pulls the
+peers' shards straight into the pyramid the forward kernel reads, and the backward kernel accumulates its partial
+``grad_img`` directly in the symmetric buffer the peers' reduce-scatter kernels read -- no staging copies, one launch per
+collective, flags instead of host-side synchronisation.
 """
 from __future__ import annotations
 
+import ctypes
 from typing import Optional, Tuple
 
 import torch
 import torch.distributed as dist
 
+from . import _lib, kernels
 from .frontend import multiscale_deformable_attention
 
 
@@ -137,3 +143,108 @@ def all_reduce_grad_img_(grad_img: torch.Tensor, group=None) -> torch.Tensor:
     gradient): in-place sum of the per-rank partial grad_img."""
     dist.all_reduce(grad_img, op=dist.ReduceOp.SUM, group=group)
     return grad_img
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# NVLink peer-memory route (one process per GPU of one node; torch symmetric memory provides the peer mappings)
+# ---------------------------------------------------------------------------------------------------------------------
+class PeerPixelExchange:
+    """Buffers and flags for query-sharded MSDA over peer memory, for a fixed problem size (fp32).
+
+    Allocates, in symmetric memory: the staging pixel shard ``[B, chunk, H, D]`` the peers pull in the all-gather, this
+    rank's partial ``grad_img`` ``[B, world * chunk, H, D]`` the peers pull in the reduce-scatter, and a flag block.
+    The gathered pyramid itself is an ordinary tensor.  Create it once (collective call: every rank of ``group``) and
+    reuse it for every step; the ranks must issue the same sequence of :func:`peer_query_sharded_msda` calls."""
+
+    def __init__(self, batch: int, num_pixels: int, heads: int, channels: int, group=None,
+                 device: Optional[torch.device] = None):
+        import torch.distributed._symmetric_memory as symm
+        self.group = dist.group.WORLD if group is None else group
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if self.world > 16:
+            raise ValueError("PeerPixelExchange: at most 16 ranks (one NVLink domain)")
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.device, self.num_pixels = dev, num_pixels
+        self.chunk = pixel_chunk(num_pixels, self.world)
+        self.shape_shard = (batch, self.chunk, heads, channels)
+        self.shape_full = (batch, self.world * self.chunk, heads, channels)
+        if (self.chunk * heads * channels * 4) % 16:
+            raise ValueError("PeerPixelExchange: a pixel chunk must be a multiple of 16 bytes")
+        name = self.group.group_name
+        self.staging = symm.empty(self.shape_shard, dtype=torch.float32, device=dev)
+        self.partial = symm.empty(self.shape_full, dtype=torch.float32, device=dev)
+        self.flags = symm.empty((4 * 16,), dtype=torch.int32, device=dev)
+        self.flags.zero_()
+        self._handles = [symm.rendezvous(t, name) for t in (self.staging, self.partial, self.flags)]
+        self.counters = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.full = torch.empty(self.shape_full, dtype=torch.float32, device=dev)
+        arr = ctypes.c_void_p * self.world
+        self._ptrs = [arr(*[int(p) for p in h.buffer_ptrs]) for h in self._handles]   # keep the host arrays alive
+        self.ctx = _lib.MsdaPeerCtx(self.world, self.rank,
+                                    ctypes.cast(self._ptrs[0], ctypes.POINTER(ctypes.c_void_p)),
+                                    ctypes.cast(self._ptrs[1], ctypes.POINTER(ctypes.c_void_p)),
+                                    ctypes.cast(self._ptrs[2], ctypes.POINTER(ctypes.c_void_p)),
+                                    ctypes.c_void_p(self.counters.data_ptr()))
+        self.n_all_gather = 0
+        self.n_reduce_scatter = 0
+        torch.cuda.synchronize(dev)
+        self._handles[2].barrier(channel=0)      # every rank's flags are zero before anybody signals
+        torch.cuda.synchronize(dev)
+
+    def all_gather(self, shard: torch.Tensor) -> torch.Tensor:
+        """[B, chunk, H, D] pixel shard of this rank -> the padded pyramid [B, world * chunk, H, D] (self.full)."""
+        if tuple(shard.shape) != self.shape_shard or shard.dtype != torch.float32 or not shard.is_contiguous():
+            raise ValueError(f"PeerPixelExchange.all_gather: expected a contiguous fp32 {self.shape_shard} shard")
+        self.n_all_gather += 1
+        per_image = self.chunk * self.shape_shard[2] * self.shape_shard[3] * 4
+        rc = _lib.get_lib().msda_peer_all_gather(
+            self.full.data_ptr(), shard.data_ptr(), ctypes.byref(self.ctx), self.shape_shard[0], per_image,
+            self.n_all_gather, self.n_reduce_scatter, torch.cuda.current_stream(self.device).cuda_stream)
+        if rc:
+            _lib.check(rc, "msda_peer_all_gather")
+        return self.full
+
+    def reduce_scatter(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Sum over the ranks of their partial grad_img (self.partial), this rank's pixel chunk: [B, chunk, H, D]."""
+        if out is None:
+            out = torch.empty(self.shape_shard, dtype=torch.float32, device=self.device)
+        self.n_reduce_scatter += 1
+        per_image = self.chunk * self.shape_shard[2] * self.shape_shard[3]
+        rc = _lib.get_lib().msda_peer_reduce_scatter(
+            out.data_ptr(), ctypes.byref(self.ctx), self.shape_shard[0], per_image, self.n_reduce_scatter,
+            torch.cuda.current_stream(self.device).cuda_stream)
+        if rc:
+            _lib.check(rc, "msda_peer_reduce_scatter")
+        return out
+
+
+class _PeerQueryShardedMsda(torch.autograd.Function):
+    """all-gather (peer pull) + forward kernel; backward kernel into the symmetric partial + reduce-scatter (peer pull)."""
+
+    @staticmethod
+    def forward(ctx, img_shard, img_shapes, pts, aw, padding_mode, align_corners, ex: PeerPixelExchange):
+        full = ex.all_gather(img_shard.contiguous())
+        out = kernels.b200_multi_scale_deformable_attention_fwd(full, img_shapes, pts, aw, padding_mode, align_corners)
+        ctx.save_for_backward(img_shapes, pts, aw)
+        ctx.ex, ctx.mode = ex, (padding_mode, align_corners)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        img_shapes, pts, aw = ctx.saved_tensors
+        ex = ctx.ex
+        need_img, _, need_pts, need_aw = ctx.needs_input_grad[:4]
+        # the gathered pyramid is still in ex.full (the forward of this step wrote it; nothing else touches it)
+        _, gpts, gaw = kernels.b200_multi_scale_deformable_attention_bwd(
+            grad_out, ex.full, img_shapes, pts, aw, ctx.mode[0], ctx.mode[1],
+            needs=(True, need_pts, need_aw), deterministic=False, grads=(ex.partial, None, None))
+        gshard = ex.reduce_scatter()
+        return (gshard if need_img else None), None, gpts, gaw, None, None, None
+
+
+def peer_query_sharded_msda(exchange: PeerPixelExchange, img_shard, img_shapes, sampling_points_local,
+                            attention_weights_local, padding_mode: str, align_corners: bool) -> torch.Tensor:
+    """:func:`query_sharded_msda` over NVLink peer memory (fp32, CUDA): same inputs / outputs / gradients."""
+    return _PeerQueryShardedMsda.apply(img_shard, img_shapes, sampling_points_local, attention_weights_local,
+                                       padding_mode, align_corners, exchange)

@@ -69,6 +69,24 @@ def _worker(rank, world, port, backend, device_kind, results):
         want = D.shard_pixels(a.grad, rank, world)
         assert shard.grad.shape == (B, chunk, H, Dh)
         torch.testing.assert_close(shard.grad, want, rtol=1e-5, atol=1e-5)
+        if device_kind == "cuda":
+            # --- the same over NVLink peer memory (library kernels instead of NCCL), several steps in a row ---
+            ex = D.PeerPixelExchange(B, npix, H, Dh)
+            for step in range(3):
+                sh2 = D.shard_pixels(img, rank, world).clone().requires_grad_(True)
+                pq2, wq2 = (D.shard_queries(t, rank, world).clone().requires_grad_(True) for t in (pts, aw))
+                out_p = D.peer_query_sharded_msda(ex, sh2, s, pq2, wq2, pm, ac)
+                out_p.backward(D.shard_queries(go, rank, world).contiguous())
+                assert torch.equal(out_p, out_q), f"peer forward differs (step {step})"
+                assert torch.equal(pq2.grad, pq.grad) and torch.equal(wq2.grad, wq.grad)
+                torch.testing.assert_close(sh2.grad, want, rtol=1e-5, atol=1e-5)
+            # forward only, twice (no reduce-scatter in between): the staging shard is re-used safely
+            with torch.no_grad():
+                for _ in range(2):
+                    o = D.peer_query_sharded_msda(ex, D.shard_pixels(img, rank, world).contiguous(), s, pq2.detach(),
+                                                  wq2.detach(), pm, ac)
+                assert torch.equal(o, out_q)
+            torch.cuda.synchronize()
         results[rank] = "ok"
     except Exception as ex:  # noqa: BLE001
         import traceback
