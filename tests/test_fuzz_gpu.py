@@ -39,10 +39,19 @@ def test_random_problem_matches_oracle(seed):
     rgi, rgp, rga = msda_oracle.backward(go, img, s, pts, aw, pm, ac)
     what = f"seed {seed}: B={B} Q={Q} H={H} D={D} shapes={shapes} K={K} {pm}/{ac} {points} {dtype}"
     if dtype == torch.float32:
-        tol = (1e-5, 2e-6, 1e-4, 1e-5)
+        tol = (1e-5, 1e-6, 1e-4, 1e-5)
     else:
         tol = (1e-9, 1e-10, 1e-9, 1e-10)
-    assert_close(to_np(out), ref_out, tol[0], tol[1] * max(1.0, np.abs(ref_out).max()), what + " out")
+    # Forward bar of BASELINE.json: rtol 1e-5 / atol 1e-6.  Two correct fp32 evaluations of out = sum_i w_i v_i (n = 4 L K
+    # terms; the kernel and the oracle use the same coordinate arithmetic but another summation order and FMA
+    # contraction) can differ by up to ~n u sum_i |w_i v_i| (u = 2^-24), so the absolute term is applied PER ELEMENT
+    # relative to that sum, S = forward(|img|, |weights|): atol_e = 1e-6 * max(1, S_e).  For O(1) data (S <= 1: weights
+    # sum to one, |img| ~ 0.8) this IS the unscaled 1e-6; only elements whose terms are larger get proportionally more.
+    S = msda_oracle.forward(img.abs(), s, pts, aw.abs(), pm, ac)
+    err = np.abs(to_np(out).astype(np.float64) - ref_out)
+    lim = tol[0] * np.abs(ref_out) + tol[1] * np.maximum(1.0, S)
+    assert (err <= lim).all(), f"{what} out: {int((err > lim).sum())} elements outside rtol 1e-5 / atol 1e-6 max(1, sum|w v|); " \
+                               f"worst {float((err - lim).max()):.3e} over the limit"
     for t, r, n in ((gi, rgi, "grad_img"), (gp, rgp, "grad_points"), (ga, rga, "grad_weights")):
         assert_close(to_np(t), r, tol[2], tol[3] * max(1e-30, np.abs(r).max()), f"{what} {n}")
 
