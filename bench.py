@@ -438,7 +438,7 @@ def time_module(flush, steps=20):
     return res
 
 
-def l2_probe(K_lib):
+def l2_probe(K_lib, kinds=("gather", "scatter")):
     """Random 128-byte-row gather / red.add.v4 throughput over an L2-resident 32 MiB buffer (the access shape of the
     kernels) -- the 'L2 gather roof' SURVEY.md 8d asks to measure next to every result."""
     import ctypes
@@ -449,7 +449,7 @@ def l2_probe(K_lib):
     n = 64 * 1024 * 1024 // 8   # 8.4M rows = 1 GiB of row traffic
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     res = {}
-    for kind in ("gather", "scatter"):
+    for kind in kinds:
         def launch(seed):
             if kind == "gather":
                 return lib.msda_probe_gather(ctypes.c_void_p(sink.data_ptr()), ctypes.c_void_p(buf.data_ptr()),

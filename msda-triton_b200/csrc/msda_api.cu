@@ -483,20 +483,25 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
 // One 8-lane group per 128-byte row, 8 independent rows in flight per lane: the access shape of the MSDA gathers.
 __global__ void __launch_bounds__(512) probe_gather_kernel(float *__restrict__ sink, const float *__restrict__ buf,
                                                            long long buf_rows, long long rows, uint32_t seed) {
+    // Row indices by multiplicative hashing (two integer instructions per row: the first version spent 15 on a full
+    // avalanche hash and was ALU-bound at 71 % of the pipe, i.e. it measured its own index arithmetic), 16 independent
+    // 128-bit loads in flight per lane, 8 lanes per 128-byte row like the kernels' gathers.
     const int j = threadIdx.x & 7;
     const long long group = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     const long long ngroups = ((long long)gridDim.x * blockDim.x) >> 3;
+    int shift = 0;                                     // buf_rows is rounded down to a power of two
+    while ((2ll << shift) <= buf_rows) ++shift;
+    const unsigned down = 32u - (unsigned)shift;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (long long r = group * 8; r < rows; r += ngroups * 8) {
-        float4 v[8];
+    for (long long r = group * 16; r < rows; r += ngroups * 16) {
+        float4 v[16];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const uint32_t hsh = mix32((uint32_t)(r + i) * 2654435761U + seed);
-            const long long row = (long long)(((unsigned long long)hsh * (unsigned long long)buf_rows) >> 32);
-            v[i] = __ldg(reinterpret_cast<const float4 *>(buf + row * 32 + j * 4));
+        for (int i = 0; i < 16; ++i) {
+            const uint32_t row = (((uint32_t)r + (uint32_t)i) * 2654435761U + seed) >> down;
+            v[i] = __ldg(reinterpret_cast<const float4 *>(buf + (size_t)row * 32 + j * 4));
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 16; ++i) {
             acc.x += v[i].x;
             acc.y += v[i].y;
             acc.z += v[i].z;

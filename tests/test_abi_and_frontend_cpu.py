@@ -35,7 +35,16 @@ def test_header_declares_the_expected_entry_points():
     assert declared_symbols() == sorted([
         "msda_abi_version", "msda_last_error", "msda_forward", "msda_backward_workspace_bytes", "msda_backward",
         "msda_level_table", "msda_probe_gather", "msda_probe_scatter", "msda_module_supported", "msda_module_forward",
-        "msda_module_backward", "msda_reload_tuning"])
+        "msda_module_backward", "msda_reload_tuning", "msda_peer_all_gather", "msda_peer_reduce_scatter"])
+
+
+def test_peer_entry_points_validate_without_a_gpu(libpath):
+    """The peer-memory collectives reject a malformed context before touching the device."""
+    from msda_triton import _lib
+    lib = _lib.get_lib()
+    ctx = _lib.MsdaPeerCtx(0, 0, None, None, None, None)          # world = 0
+    assert lib.msda_peer_all_gather(None, None, ctypes.byref(ctx), 1, 16, 1, 0, None) < 0
+    assert lib.msda_peer_reduce_scatter(None, ctypes.byref(ctx), 1, 4, 1, None) < 0
 
 
 def test_library_exports_every_declared_symbol(libpath):
@@ -60,7 +69,12 @@ def test_argument_validation_needs_no_gpu(libpath):
     assert lib.msda_backward_workspace_bytes(ctypes.byref(ok), 7) == 2 * 5440 * 8 * 32 * 4
     ok32 = _lib.MsdaProblem(2, 5440, 8, 32, 100, 4, 4, _lib.DTYPE_F32, 0, 0, 0)
     assert lib.msda_backward_workspace_bytes(ctypes.byref(ok32), 7) == 0
-    assert lib.msda_backward_workspace_bytes(ctypes.byref(ok32), 7 | 8) >= 4 * 4 * (2 * 100 * 8 * 16 * 4)
+    # deterministic mode: exact row adds on the tuned fp32 shapes (a 64-bit bound per pyramid row + a float per unit) ...
+    det = lib.msda_backward_workspace_bytes(ctypes.byref(ok32), 7 | 8)
+    assert 8 * (2 * 5440 * 8) + 4 * (2 * 100 * 8) <= det < 2 << 20
+    # ... the sorted-segment path everywhere else (24 bytes per bilinear corner)
+    odd = _lib.MsdaProblem(2, 5440, 8, 24, 100, 4, 4, _lib.DTYPE_F32, 0, 0, 0)
+    assert lib.msda_backward_workspace_bytes(ctypes.byref(odd), 7 | 8) >= 4 * 4 * (2 * 100 * 8 * 16 * 4)
 
 
 def test_static_module_rule_agrees_with_library(libpath):
