@@ -243,9 +243,43 @@ __global__ void round_grad_img_kernel(T *__restrict__ dst, const float *__restri
     }
 }
 
+// Natural channel order, everything 16-byte aligned: eight elements per thread and step -- two streaming 128-bit loads,
+// one 128-bit store.  (The element-wise kernel above ran the B=8 x 22 223-pixel decoder pyramid, 182 MB of fp32 in,
+// 91 MB out, in 117 us = 2.3 TB/s; this one is bound by HBM.)
+template <typename T>
+__global__ void __launch_bounds__(256) round_grad_img_vec8_kernel(T *__restrict__ dst, const float *__restrict__ src,
+                                                                  long long n8) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+        const float4 a = __ldcs(reinterpret_cast<const float4 *>(src) + 2 * i);
+        const float4 b = __ldcs(reinterpret_cast<const float4 *>(src) + 2 * i + 1);
+        Pack<T, 8> o;
+        o.v[0] = Traits<T>::from_ct(a.x);
+        o.v[1] = Traits<T>::from_ct(a.y);
+        o.v[2] = Traits<T>::from_ct(a.z);
+        o.v[3] = Traits<T>::from_ct(a.w);
+        o.v[4] = Traits<T>::from_ct(b.x);
+        o.v[5] = Traits<T>::from_ct(b.y);
+        o.v[6] = Traits<T>::from_ct(b.z);
+        o.v[7] = Traits<T>::from_ct(b.w);
+        reinterpret_cast<Pack<T, 8> *>(dst)[i] = o;
+    }
+}
+
 cudaError_t launch_round_grad_img(void *dst, const float *src, long long n, int dtype, int D, int permuted_lanes,
                                   cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
+    if (permuted_lanes == 0 && n % 8 == 0 && reinterpret_cast<uintptr_t>(dst) % 16 == 0 &&
+        reinterpret_cast<uintptr_t>(src) % 16 == 0 && (dtype == 1 || dtype == 2)) {
+        const long long n8 = n / 8;
+        long long want8 = (n8 + 255) / 256;
+        const int grid8 = (int)(want8 > 148 * 16 ? 148 * 16 : want8);
+        if (dtype == 1)
+            round_grad_img_vec8_kernel<__half><<<grid8, 256, 0, st>>>(static_cast<__half *>(dst), src, n8);
+        else
+            round_grad_img_vec8_kernel<__nv_bfloat16><<<grid8, 256, 0, st>>>(static_cast<__nv_bfloat16 *>(dst), src, n8);
+        return cudaGetLastError();
+    }
     const int threads = 256;
     long long want = (n + threads - 1) / threads;
     const int grid = (int)(want > 148 * 32 ? 148 * 32 : want);

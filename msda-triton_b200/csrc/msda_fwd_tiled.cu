@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     const unsigned row_bytes = (unsigned)(a.H * a.D) * (unsigned)sizeof(T);
 
     const int tiles_per_bh = ws.tiles_per_bh;
+    const unsigned streamed = stream_slot_mask(a, s_lv, a.D * (int)sizeof(T), ws.l1_keep_bytes, LK);
     for (int wave = 0; wave < ws.waves; ++wave) {
     int t_begin, t_end;
     wave_range(ws, wave, blockIdx.x, gridDim.x, t_begin, t_end);
@@ -95,8 +96,13 @@ __global__ void __launch_bounds__(THREADS, 1)
                     // corner rows are clamped into the level, so all four gathers are always in range; zeros padding
                     // (kernels.py:227-231: out-of-range corners read as 0) is applied when the values are consumed,
                     // which keeps the 4*NB loads independent and in flight together
+                    if ((streamed >> (src * PPL + pp)) & 1u) {   // warp-uniform: a level that cannot live in L1
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) raw[n][c] = gather_slice<VECB>(lane_base, o[c]);
+                        for (int c = 0; c < 4; ++c) raw[n][c] = gather_slice<VECB, true>(lane_base, o[c]);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) raw[n][c] = gather_slice<VECB>(lane_base, o[c]);
+                    }
                 }
 #pragma unroll
                 for (int n = 0; n < NB; ++n) {
@@ -138,7 +144,7 @@ static cudaError_t launch_tiled_cfg(const KernelArgs &a, int sm_count, cudaStrea
     const int warps = THREADS / 32;
     const int want = (total_tiles + warps - 1) / warps;
     const int grid = (int)(want < sm_count ? (want < 1 ? 1 : want) : sm_count);
-    WaveSchedule ws = make_wave_schedule(a, tiles_per_bh, sizeof(T), kFwdL2Budget);
+    WaveSchedule ws = make_wave_schedule(a, tiles_per_bh, sizeof(T), kFwdL2Budget, 4LL * warps * grid);
     // many waves of substantial size: keep the persistent CTAs on the same wave (wave_pace).  Waves with only a few
     // tiles per warp (decoder: 900 queries against a 22k-pixel pyramid) cannot drift far and would only pay the
     // per-wave handshake (measured on that shape: module step 0.93 -> 1.14 ms when paced).

@@ -50,6 +50,8 @@ struct WaveSchedule {
     int waves;
     unsigned *pace;        // arrival counter of this launch (zeroed on the stream before it), nullptr = no pacing
     int pace_slack;        // waves a CTA may run ahead of the slowest CTA
+    long long l1_keep_bytes;   // pyramid bytes per (b,h) slice the gathers may keep in L1 (finer levels are streamed); < 0: off
+    int bwd_stream;            // backward: stream as the forward does (tuning knob, off by default)
 };
 
 // Wave pacing.  The CTAs of the persistent grid walk the waves independently; over many waves (B=64: 64 waves) the
@@ -117,7 +119,13 @@ __device__ __forceinline__ void wave_pace_cta(const WaveSchedule &w, int wave) {
     __syncthreads();
 }
 
-inline WaveSchedule make_wave_schedule(const KernelArgs &a, int tiles_per_bh, size_t elem_size, size_t l2_budget_bytes) {
+// min_tiles_per_wave: with few queries per image (decoder: 900 queries against a 22k-pixel pyramid) one image is less
+// than one tile per warp and the persistent grid idles at every wave boundary; a wave is then grown, up to
+// kWaveHardCapBytes of L2, until it holds that many tiles (B=8 x Q=900 fp32 forward: 78.8 -> 53 us).
+constexpr unsigned long long kWaveHardCapBytes = 96ull << 20;
+
+inline WaveSchedule make_wave_schedule(const KernelArgs &a, int tiles_per_bh, size_t elem_size, size_t l2_budget_bytes,
+                                       long long min_tiles_per_wave = 0) {
     WaveSchedule w;
     w.tiles_per_bh = tiles_per_bh;
     w.slices = a.B * a.H;
@@ -127,12 +135,17 @@ inline WaveSchedule make_wave_schedule(const KernelArgs &a, int tiles_per_bh, si
     const unsigned long long image_bytes = (unsigned long long)a.Npix * a.H * a.D * elem_size;
     long long images = (long long)(l2_budget_bytes / (image_bytes ? image_bytes : 1));
     if (images < 1) images = 1;
+    while (images * a.H * tiles_per_bh < min_tiles_per_wave && images < a.B &&
+           (unsigned long long)(images + 1) * image_bytes <= kWaveHardCapBytes)
+        ++images;
     long long max_slices = images * a.H;
     if (tuning().slices_per_wave > 0) max_slices = tuning().slices_per_wave;   // tuning knob
     if (max_slices > w.slices) max_slices = w.slices;
     w.waves = (int)((w.slices + max_slices - 1) / max_slices);
     w.slices_per_wave = (int)max_slices;
     w.pace = nullptr;
+    w.l1_keep_bytes = tuning().l1_keep_kb < 0 ? -1 : (long long)tuning().l1_keep_kb * 1024;   // tuning knob
+    w.bwd_stream = tuning().bwd_stream;
     const int slack = tuning().pace_slack;   // tuning knob
     w.pace_slack = slack < 0 ? 0 : (slack > kPaceMaxSlack ? kPaceMaxSlack : slack);
     return w;
@@ -358,19 +371,61 @@ template <> struct RawSlice<8> { using type = uint2; };
 struct alignas(32) Raw256 { uint4 lo, hi; };
 template <> struct RawSlice<32> { using type = Raw256; };   // sm_100: LDG.E.256
 
-template <int BYTES>
+// NA = "no allocate": the row is served through L1 without being written into it (LDG.E.NA).  Used for the pyramid
+// levels that cannot stay resident in L1 anyway (see stream_slot_mask): their lines then neither spend an L1 fill
+// wavefront nor evict the coarse levels that do fit.
+template <int BYTES, bool NA = false>
 __device__ __forceinline__ typename RawSlice<BYTES>::type gather_slice(const unsigned char *__restrict__ lane_base,
                                                                        unsigned byte_off) {
-    return __ldg(reinterpret_cast<const typename RawSlice<BYTES>::type *>(lane_base + byte_off));
+    if constexpr (!NA) {
+        if constexpr (BYTES == 32) {
+            Raw256 r;
+            asm("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                : "=r"(r.lo.x), "=r"(r.lo.y), "=r"(r.lo.z), "=r"(r.lo.w), "=r"(r.hi.x), "=r"(r.hi.y), "=r"(r.hi.z), "=r"(r.hi.w)
+                : "l"(lane_base + byte_off));
+            return r;
+        } else {
+            return __ldg(reinterpret_cast<const typename RawSlice<BYTES>::type *>(lane_base + byte_off));
+        }
+    } else {
+        if constexpr (BYTES == 32) {
+            Raw256 r;
+            asm("ld.global.nc.L1::no_allocate.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                : "=r"(r.lo.x), "=r"(r.lo.y), "=r"(r.lo.z), "=r"(r.lo.w), "=r"(r.hi.x), "=r"(r.hi.y), "=r"(r.hi.z), "=r"(r.hi.w)
+                : "l"(lane_base + byte_off));
+            return r;
+        } else if constexpr (BYTES == 16) {
+            uint4 r;
+            asm("ld.global.nc.L1::no_allocate.v4.b32 {%0, %1, %2, %3}, [%4];"
+                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                : "l"(lane_base + byte_off));
+            return r;
+        } else {
+            uint2 r;
+            asm("ld.global.nc.L1::no_allocate.v2.b32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(lane_base + byte_off));
+            return r;
+        }
+    }
 }
 
-template <>
-__device__ __forceinline__ Raw256 gather_slice<32>(const unsigned char *__restrict__ lane_base, unsigned byte_off) {
-    Raw256 r;
-    asm("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-        : "=r"(r.lo.x), "=r"(r.lo.y), "=r"(r.lo.z), "=r"(r.lo.w), "=r"(r.hi.x), "=r"(r.hi.y), "=r"(r.hi.z), "=r"(r.hi.w)
-        : "l"(lane_base + byte_off));
-    return r;
+// Bit p set = the level of point slot p is STREAMED (gathered with no-allocate loads).  Walking up from the coarsest
+// level, levels are kept while the rows of one (b,h) slice of all kept levels fit `keep_bytes` of L1 (benchmark
+// pyramid, fp32: 8x8 + 16x16 + 32x32 = 168 KB kept, 64x64 = 512 KB streamed); everything finer is streamed.
+// keep_bytes < 0 switches streaming off.  Uniform over the grid; call once per kernel.
+__device__ __forceinline__ unsigned stream_slot_mask(const KernelArgs &a, const Level *s_lv, int row_bytes_per_head,
+                                                     long long keep_bytes, int slots) {
+    if (keep_bytes < 0) return 0u;
+    int first_kept = a.L;
+    long long cum = 0;
+    for (int l = a.L - 1; l >= 0; --l) {
+        cum += (long long)s_lv[l].h * s_lv[l].w * row_bytes_per_head;
+        if (cum > keep_bytes) break;
+        first_kept = l;
+    }
+    unsigned mask = 0u;
+    for (int p = 0; p < slots && p < 32; ++p)
+        if (slot_level(p, a) < first_kept) mask |= 1u << p;
+    return mask;
 }
 
 __device__ __forceinline__ uint4 gather_row(const unsigned char *__restrict__ lane_base, unsigned byte_off) {
