@@ -69,10 +69,6 @@ __global__ void __launch_bounds__(THREADS, 1)
     constexpr unsigned kAccScale = sizeof(float) / sizeof(T);  // accumulation row bytes / storage row bytes
 
     const int tiles_per_bh = ws.tiles_per_bh;
-    // no-allocate gathers of the levels that cannot stay in L1 (forward: -15 %) are neutral to slightly negative here -- the
-    // backward is bound by its row adds, which do not allocate in L1 anyway -- so they stay opt-in (MSDA_B200_BWD_STREAM=1)
-    const unsigned streamed = (SPLIT || !ws.bwd_stream) ? 0u
-                              : stream_slot_mask(a, s_lv, a.D * (int)sizeof(T), ws.l1_keep_bytes, LK);
     const int subs = SPLIT ? subs_arg : 1;
     static_assert(!(SPLIT && FUSED), "the fused module core is instantiated for L*K == 16 only");
     for (int wave = 0; wave < ws.waves; ++wave) {
@@ -147,14 +143,10 @@ __global__ void __launch_bounds__(THREADS, 1)
                     corner_offsets(off, pack, row_bytes, o[n]);
                     msk[n] = BORDER ? 0xFu : ((pack >> kPackMaskShift) & 0xFu);
                     // always in range (clamped rows); zeros padding is applied to the dot products below
-                    if ((streamed >> ((jj0 + n) * PPL + pp)) & 1u) {   // warp-uniform: a level that cannot live in L1
+                    // (no-allocate gathers of the levels that cannot stay in L1, the forward's -15 %, measured neutral to
+                    // slightly negative here: the backward is bound by its row adds, which never allocate in L1)
 #pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            raw[n][c] = gather_slice<VEC * (int)sizeof(T), true>(lane_base, o[n][c]);
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) raw[n][c] = gather_slice<VEC * (int)sizeof(T)>(lane_base, o[n][c]);
-                    }
+                    for (int c = 0; c < 4; ++c) raw[n][c] = gather_slice<VEC * (int)sizeof(T)>(lane_base, o[n][c]);
                 }
 #pragma unroll
                 for (int n = 0; n < NB; ++n) {

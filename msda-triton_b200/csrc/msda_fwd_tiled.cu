@@ -19,7 +19,9 @@ constexpr size_t kFwdL2Budget = 24u << 20;
 // points; softmax and the sampling-point arithmetic happen in registers, sampling_points / attention_weights are never
 // materialised.
 // PADDED = the unit has a.LK <= LK points; the LK - a.LK trailing slots are skipped (warp-uniformly) by every loop.
-template <typename T, int LANES, int LK, bool BORDER, int NB, int THREADS, bool FUSED, bool PADDED, int VECB = 16>
+// NA     = the first NA point slots (the finest levels) are gathered with no-allocate loads (streamed_points()).
+template <typename T, int LANES, int LK, bool BORDER, int NB, int THREADS, bool FUSED, bool PADDED, int VECB = 16,
+          int NA = 0>
 __global__ void __launch_bounds__(THREADS, 1)
     msda_fwd_tiled_kernel(const KernelArgs a, const WaveSchedule ws) {
     using Cfg = TiledCfg<T, LANES, LK, VECB>;
@@ -41,7 +43,6 @@ __global__ void __launch_bounds__(THREADS, 1)
     const unsigned row_bytes = (unsigned)(a.H * a.D) * (unsigned)sizeof(T);
 
     const int tiles_per_bh = ws.tiles_per_bh;
-    const unsigned streamed = stream_slot_mask(a, s_lv, a.D * (int)sizeof(T), ws.l1_keep_bytes, LK);
     for (int wave = 0; wave < ws.waves; ++wave) {
     int t_begin, t_end;
     wave_range(ws, wave, blockIdx.x, gridDim.x, t_begin, t_end);
@@ -96,12 +97,12 @@ __global__ void __launch_bounds__(THREADS, 1)
                     // corner rows are clamped into the level, so all four gathers are always in range; zeros padding
                     // (kernels.py:227-231: out-of-range corners read as 0) is applied when the values are consumed,
                     // which keeps the 4*NB loads independent and in flight together
-                    if ((streamed >> (src * PPL + pp)) & 1u) {   // warp-uniform: a level that cannot live in L1
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) raw[n][c] = gather_slice<VECB, true>(lane_base, o[c]);
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) raw[n][c] = gather_slice<VECB>(lane_base, o[c]);
+                    for (int c = 0; c < 4; ++c) {
+                        if (src * PPL + pp < NA)   // (constant after unrolling) a level that cannot live in L1: do not allocate
+                            raw[n][c] = gather_slice_na<VECB>(lane_base, o[c]);
+                        else
+                            raw[n][c] = gather_slice<VECB>(lane_base, o[c]);
                     }
                 }
 #pragma unroll
@@ -135,8 +136,24 @@ __global__ void __launch_bounds__(THREADS, 1)
     }  // waves
 }
 
-template <typename T, int LANES, int LK, int THREADS, int NB, bool FUSED = false, bool PADDED = false, int VECB = 16>
+template <typename T, int LANES, int LK, int THREADS, int NB, bool FUSED = false, bool PADDED = false, int VECB = 16,
+          int NA = -1>
 static cudaError_t launch_tiled_cfg(const KernelArgs &a, int sm_count, cudaStream_t st) {
+    if constexpr (NA < 0) {
+        // 16 exact slots, K == 4: instantiations that stream the first 0 / 4 / 8 / 12 points (whole levels)
+        if constexpr (LK == 16 && !PADDED) {
+            if (a.K == 4 && a.L == 4) {
+                switch (streamed_points(a, (size_t)a.D * sizeof(T))) {
+                    case 4: return launch_tiled_cfg<T, LANES, LK, THREADS, NB, FUSED, PADDED, VECB, 4>(a, sm_count, st);
+                    case 8: return launch_tiled_cfg<T, LANES, LK, THREADS, NB, FUSED, PADDED, VECB, 8>(a, sm_count, st);
+                    case 12: return launch_tiled_cfg<T, LANES, LK, THREADS, NB, FUSED, PADDED, VECB, 12>(a, sm_count, st);
+                    default: break;
+                }
+            }
+        }
+        return launch_tiled_cfg<T, LANES, LK, THREADS, NB, FUSED, PADDED, VECB, 0>(a, sm_count, st);
+    } else {
+    constexpr int NAK = NA;
     constexpr int G = TiledCfg<T, LANES, LK, VECB>::G;
     if (!tiled_offsets_fit(a, sizeof(T))) return cudaErrorNotSupported;
     const int tiles_per_bh = (a.Q + G - 1) / G;
@@ -154,10 +171,11 @@ static cudaError_t launch_tiled_cfg(const KernelArgs &a, int sm_count, cudaStrea
         if (e != cudaSuccess) return e;
     }
     if (a.border)
-        msda_fwd_tiled_kernel<T, LANES, LK, true, NB, THREADS, FUSED, PADDED, VECB><<<grid, THREADS, 0, st>>>(a, ws);
+        msda_fwd_tiled_kernel<T, LANES, LK, true, NB, THREADS, FUSED, PADDED, VECB, NAK><<<grid, THREADS, 0, st>>>(a, ws);
     else
-        msda_fwd_tiled_kernel<T, LANES, LK, false, NB, THREADS, FUSED, PADDED, VECB><<<grid, THREADS, 0, st>>>(a, ws);
+        msda_fwd_tiled_kernel<T, LANES, LK, false, NB, THREADS, FUSED, PADDED, VECB, NAK><<<grid, THREADS, 0, st>>>(a, ws);
     return cudaGetLastError();
+    }
 }
 
 // Launch shape.  Measured on B200 (cold L2, fp32 D=32): 1024 threads x 2-point gather batches (64 registers) versus

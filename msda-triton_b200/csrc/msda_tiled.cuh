@@ -50,8 +50,6 @@ struct WaveSchedule {
     int waves;
     unsigned *pace;        // arrival counter of this launch (zeroed on the stream before it), nullptr = no pacing
     int pace_slack;        // waves a CTA may run ahead of the slowest CTA
-    long long l1_keep_bytes;   // pyramid bytes per (b,h) slice the gathers may keep in L1 (finer levels are streamed); < 0: off
-    int bwd_stream;            // backward: stream as the forward does (tuning knob, off by default)
 };
 
 // Wave pacing.  The CTAs of the persistent grid walk the waves independently; over many waves (B=64: 64 waves) the
@@ -144,8 +142,6 @@ inline WaveSchedule make_wave_schedule(const KernelArgs &a, int tiles_per_bh, si
     w.waves = (int)((w.slices + max_slices - 1) / max_slices);
     w.slices_per_wave = (int)max_slices;
     w.pace = nullptr;
-    w.l1_keep_bytes = tuning().l1_keep_kb < 0 ? -1 : (long long)tuning().l1_keep_kb * 1024;   // tuning knob
-    w.bwd_stream = tuning().bwd_stream;
     const int slack = tuning().pace_slack;   // tuning knob
     w.pace_slack = slack < 0 ? 0 : (slack > kPaceMaxSlack ? kPaceMaxSlack : slack);
     return w;
@@ -371,61 +367,47 @@ template <> struct RawSlice<8> { using type = uint2; };
 struct alignas(32) Raw256 { uint4 lo, hi; };
 template <> struct RawSlice<32> { using type = Raw256; };   // sm_100: LDG.E.256
 
-// NA = "no allocate": the row is served through L1 without being written into it (LDG.E.NA).  Used for the pyramid
-// levels that cannot stay resident in L1 anyway (see stream_slot_mask): their lines then neither spend an L1 fill
-// wavefront nor evict the coarse levels that do fit.
-template <int BYTES, bool NA = false>
+// Plain read-only gather of one lane's slice of a corner row.
+template <int BYTES>
 __device__ __forceinline__ typename RawSlice<BYTES>::type gather_slice(const unsigned char *__restrict__ lane_base,
                                                                        unsigned byte_off) {
-    if constexpr (!NA) {
-        if constexpr (BYTES == 32) {
-            Raw256 r;
-            asm("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                : "=r"(r.lo.x), "=r"(r.lo.y), "=r"(r.lo.z), "=r"(r.lo.w), "=r"(r.hi.x), "=r"(r.hi.y), "=r"(r.hi.z), "=r"(r.hi.w)
-                : "l"(lane_base + byte_off));
-            return r;
-        } else {
-            return __ldg(reinterpret_cast<const typename RawSlice<BYTES>::type *>(lane_base + byte_off));
-        }
+    if constexpr (BYTES == 32) {
+        Raw256 r;
+        asm("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+            : "=r"(r.lo.x), "=r"(r.lo.y), "=r"(r.lo.z), "=r"(r.lo.w), "=r"(r.hi.x), "=r"(r.hi.y), "=r"(r.hi.z), "=r"(r.hi.w)
+            : "l"(lane_base + byte_off));
+        return r;
     } else {
-        if constexpr (BYTES == 32) {
-            Raw256 r;
-            asm("ld.global.nc.L1::no_allocate.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                : "=r"(r.lo.x), "=r"(r.lo.y), "=r"(r.lo.z), "=r"(r.lo.w), "=r"(r.hi.x), "=r"(r.hi.y), "=r"(r.hi.z), "=r"(r.hi.w)
-                : "l"(lane_base + byte_off));
-            return r;
-        } else if constexpr (BYTES == 16) {
-            uint4 r;
-            asm("ld.global.nc.L1::no_allocate.v4.b32 {%0, %1, %2, %3}, [%4];"
-                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                : "l"(lane_base + byte_off));
-            return r;
-        } else {
-            uint2 r;
-            asm("ld.global.nc.L1::no_allocate.v2.b32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(lane_base + byte_off));
-            return r;
-        }
+        return __ldg(reinterpret_cast<const typename RawSlice<BYTES>::type *>(lane_base + byte_off));
     }
 }
 
-// Bit p set = the level of point slot p is STREAMED (gathered with no-allocate loads).  Walking up from the coarsest
-// level, levels are kept while the rows of one (b,h) slice of all kept levels fit `keep_bytes` of L1 (benchmark
-// pyramid, fp32: 8x8 + 16x16 + 32x32 = 168 KB kept, 64x64 = 512 KB streamed); everything finer is streamed.
-// keep_bytes < 0 switches streaming off.  Uniform over the grid; call once per kernel.
-__device__ __forceinline__ unsigned stream_slot_mask(const KernelArgs &a, const Level *s_lv, int row_bytes_per_head,
-                                                     long long keep_bytes, int slots) {
-    if (keep_bytes < 0) return 0u;
-    int first_kept = a.L;
-    long long cum = 0;
-    for (int l = a.L - 1; l >= 0; --l) {
-        cum += (long long)s_lv[l].h * s_lv[l].w * row_bytes_per_head;
-        if (cum > keep_bytes) break;
-        first_kept = l;
+// The same gather served through L1 WITHOUT being written into it (LDG.E.NA).  Used for the pyramid levels that cannot
+// stay resident in L1 anyway (see streamed_points): their lines then neither spend an L1 fill wavefront nor evict the
+// coarse levels that do fit.  The choice is a COMPILE-TIME property of the point slot (template parameter of the
+// kernels): as a run-time branch the two flavours were joined by one predicated MOV per loaded register (20 % of the
+// forward's instructions), and as a predicated pair in one asm statement the second load waits for the first one's
+// destination registers (7x slower).
+template <int BYTES>
+__device__ __forceinline__ typename RawSlice<BYTES>::type gather_slice_na(const unsigned char *__restrict__ lane_base,
+                                                                          unsigned byte_off) {
+    if constexpr (BYTES == 32) {
+        Raw256 r;
+        asm("ld.global.nc.L1::no_allocate.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+            : "=r"(r.lo.x), "=r"(r.lo.y), "=r"(r.lo.z), "=r"(r.lo.w), "=r"(r.hi.x), "=r"(r.hi.y), "=r"(r.hi.z), "=r"(r.hi.w)
+            : "l"(lane_base + byte_off));
+        return r;
+    } else if constexpr (BYTES == 16) {
+        uint4 r;
+        asm("ld.global.nc.L1::no_allocate.v4.b32 {%0, %1, %2, %3}, [%4];"
+            : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+            : "l"(lane_base + byte_off));
+        return r;
+    } else {
+        uint2 r;
+        asm("ld.global.nc.L1::no_allocate.v2.b32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(lane_base + byte_off));
+        return r;
     }
-    unsigned mask = 0u;
-    for (int p = 0; p < slots && p < 32; ++p)
-        if (slot_level(p, a) < first_kept) mask |= 1u << p;
-    return mask;
 }
 
 __device__ __forceinline__ uint4 gather_row(const unsigned char *__restrict__ lane_base, unsigned byte_off) {
@@ -492,6 +474,30 @@ template <int N, int STEP> __device__ __forceinline__ void transpose_reduce(floa
         float(&lower)[HALF] = reinterpret_cast<float(&)[HALF]>(part);
         transpose_reduce<HALF, STEP / 2>(lower, j);
     }
+}
+
+// How many LEADING point slots (whole levels, finest first) the forward gathers with no-allocate loads.  The level
+// shapes live on the device, so the host models the pyramid from Npix as levels shrinking 4x each (exact for the
+// benchmark pyramid, within 5 % for 800x1333 at strides 8..64); walking up from the coarsest level, levels are kept
+// while the rows of one (b,h) slice of all kept levels fit `keep_bytes` (default 100 KB) of L1: benchmark pyramid, fp32:
+// 8x8 + 16x16 = 40 KB kept, 32x32 and 64x64 streamed; DETR pyramid: 13x21 kept.  Measured forward, keep = off / 40 KB /
+// 176 KB: bench 0.143 / 0.115 / 0.119 ms, DETR encoder 0.166 / 0.141 / 0.145 ms, DETR with local sampling points
+// 0.176 / 0.141 / 0.139 ms.  A wrong guess only costs performance.  Result in {0, K, 2K, ...}.
+inline int streamed_points(const KernelArgs &a, size_t row_bytes_per_head) {
+    const long long keep = tuning().l1_keep_kb < 0 ? -1 : (long long)tuning().l1_keep_kb * 1024;   // tuning knob
+    if (keep < 0 || a.L < 1) return 0;
+    double norm = 0.0, w = 1.0;
+    for (int l = 0; l < a.L; ++l, w *= 0.25) norm += w;
+    int first_kept = a.L;
+    double cum = 0.0;
+    for (int l = a.L - 1; l >= 0; --l) {
+        double frac = 1.0;
+        for (int i = 0; i < l; ++i) frac *= 0.25;
+        cum += (double)a.Npix * frac / norm * (double)row_bytes_per_head;
+        if (cum > (double)keep) break;
+        first_kept = l;
+    }
+    return first_kept * a.K;
 }
 
 }  // namespace msda

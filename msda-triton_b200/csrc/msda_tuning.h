@@ -16,9 +16,8 @@ struct Tuning {
                                //                                (msda_bwd_tmem.cu; default: chosen per problem)
     int tmem_warps = 15;       // MSDA_B200_TMEM_WARPS=12|15   : warps per CTA of the tensor-memory backward
     int tmem_levels = 2;       // MSDA_B200_TMEM_LEVELS=0|1|2  : at most this many of the coarsest levels go to tensor memory
-    int l1_keep_kb = 176;      // MSDA_B200_L1_KEEP_KB=n       : pyramid KB per (b,h) slice the gathers keep in L1; finer levels
+    int l1_keep_kb = 100;      // MSDA_B200_L1_KEEP_KB=n       : pyramid KB per (b,h) slice the forward keeps in L1; finer levels
                                //                                are gathered with no-allocate loads (-1: never)
-    int bwd_stream = 0;        // MSDA_B200_BWD_STREAM=1       : the backward's gathers stream the non-resident levels too
     int det_variant = -1;      // MSDA_B200_DET_VARIANT=0|1    : deterministic grad_img: 0 = radix sort, 1 = slice binning
 };
 
