@@ -46,9 +46,12 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
 __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ uint4 ld_remote(const uint4 *p) {   // no L1 allocation: the line belongs to another GPU
+// Weak (ordinary) load without L1 allocation: the line belongs to another GPU and is read once.  Ordering against the
+// producer comes from the acquire on its flag (thread 0) + __syncthreads(); system-scope RELAXED loads, the first
+// version, ran the pulls at ~360 GB/s.
+__device__ __forceinline__ uint4 ld_remote(const uint4 *p) {
     uint4 v;
-    asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
 
@@ -99,12 +102,12 @@ __global__ void __launch_bounds__(kThreads) peer_all_gather_kernel(const PeerArg
         const int p = (a.rank + d) % a.world;
         const uint4 *__restrict__ src = a.shards[p];
         long long i = tid;
-        for (; i + 3 * stride < per_peer; i += 4 * stride) {   // four loads in flight per thread
-            uint4 v[4];
+        for (; i + 7 * stride < per_peer; i += 8 * stride) {   // eight loads in flight per thread
+            uint4 v[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = ld_remote(src + i + u * stride);
+            for (int u = 0; u < 8; ++u) v[u] = ld_remote(src + i + u * stride);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 8; ++u) {
                 const long long j = i + u * stride, b = j / n16, k = j - b * n16;
                 full[(b * a.world + p) * n16 + k] = v[u];
             }
