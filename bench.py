@@ -919,21 +919,32 @@ def run_ours(args):
                 g_peak, a_peak = extra["l2_probe"]["gather_gbs"], extra["l2_probe"]["scatter_gbs"]
                 t_hbm_b, t_l2_b = bm["bwd"] / (peak * 1e9) * 1e3, bm["gather"] / (a_peak * 1e9) * 1e3
                 t_hbm_f, t_l2_f = bm["fwd"] / (peak * 1e9) * 1e3, bm["gather"] / (g_peak * 1e9) * 1e3
+                # every gathered row passes the SM's L1 data stage, one 128-byte wavefront per clock and SM (the unit ncu
+                # shows at ~80 % for the forward, l1tex__data_pipe_lsu_wavefronts, profiles/r2_ncu_summary.md)
+                props = torch.cuda.get_device_properties(local)
+                sm_hz = ((head["clocks"] or {}).get("sm_mhz") or 1965) * 1e6
+                l1_peak = props.multi_processor_count * 128 * sm_hz / 1e9
+                t_l1_f = bm["gather"] / (l1_peak * 1e9) * 1e3
                 roofline["survey_8d"] = {
-                    "definition": "roofline_time = max(compulsory_bytes / HBM_peak, corner_row_bytes / L2_peak); "
-                                  "frac = roofline_time / measured_time",
+                    "definition": "roofline_time = max(compulsory_bytes / HBM_peak, corner_row_bytes / on-chip peak of the "
+                                  "unit the rows must cross); frac = roofline_time / measured_time",
                     "bwd": {"hbm_term_ms": t_hbm_b, "l2_atomic_term_ms": t_l2_b, "roofline_ms": max(t_hbm_b, t_l2_b),
                             "measured_ms": bwd_ms, "frac": max(t_hbm_b, t_l2_b) / bwd_ms,
                             "l2_peak_gbs": a_peak,
                             "l2_peak_source": "msda_probe_scatter: red.global.add.v4.f32 of random 128-byte rows over "
-                                              "an L2-resident 32 MiB buffer, this run"},
-                    "fwd": {"hbm_term_ms": t_hbm_f, "l2_gather_term_ms": t_l2_f, "roofline_ms": max(t_hbm_f, t_l2_f),
-                            "measured_ms": fwd_ms, "frac": min(1.0, max(t_hbm_f, t_l2_f) / fwd_ms),
-                            "frac_uncapped": max(t_hbm_f, t_l2_f) / fwd_ms,
-                            "l2_peak_gbs": g_peak,
-                            "l2_peak_source": "msda_probe_gather: ld.global.nc.v4 of random 128-byte rows over an "
-                                              "L2-resident 32 MiB buffer (every row from L2), this run; the forward "
-                                              "serves 2/3 of its rows from L1, which is why it can beat this term"},
+                                              "an L2-resident 32 MiB buffer, this run; ncu of the probe: the SM's "
+                                              "L1TEX->XBAR request port at 84 % (profiles/r2_ncu_raw_probe_scatter.csv)"},
+                    "fwd": {"hbm_term_ms": t_hbm_f, "l1_pipe_term_ms": t_l1_f, "roofline_ms": max(t_hbm_f, t_l1_f),
+                            "measured_ms": fwd_ms, "frac": max(t_hbm_f, t_l1_f) / fwd_ms,
+                            "l1_pipe_peak_gbs": l1_peak,
+                            "l1_pipe_peak_source": f"{props.multi_processor_count} SMs x 128 B per clock x "
+                                                   f"{sm_hz / 1e6:.0f} MHz (SM clock sampled under load in this run)",
+                            "l2_gather_term_ms": t_l2_f, "l2_gather_peak_gbs": g_peak,
+                            "l2_gather_peak_source": "msda_probe_gather: ld.global.nc.v4 of random 128-byte rows, every "
+                                                     "row from L2, this run; ncu of the probe: L2->XBAR return path at "
+                                                     "78-84 % (profiles/r2_ncu_raw_probe_gather.csv).  Applies to the rows "
+                                                     "that miss L1 only (the forward serves about half of them from L1), "
+                                                     "so it is reported, not used as the roof"},
                     "hbm_peak_gbs": peak, "hbm_peak_source": peak_src}
             except Exception as ex:  # noqa: BLE001
                 extra["l2_probe"] = {"error": str(ex)}
