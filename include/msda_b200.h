@@ -176,22 +176,22 @@ int msda_probe_scatter(float *buf, int64_t buf_rows, int64_t rows, uint32_t seed
  *   msda_peer_all_gather      full[b, p*chunk .. (p+1)*chunk) <- rank p's pixel shard of image b, for every p
  *   msda_peer_reduce_scatter  grad_shard[b, i] <- sum over ranks r (ascending) of partial_r[b, my_rank*chunk + i]
  *
- * The epochs are the host wrapper's call counters (first call = 1): all_gather passes its own count and the number of
- * reduce_scatter calls issued so far on this rank; reduce_scatter passes its own count.  Every rank of the group must
- * issue the same sequence of calls.  The kernels spin on flags written by the peers: one launch of `SM count` CTAs.
+ * Every rank of the group must issue the same sequence of calls.  The kernels spin on flags written by the peers (one
+ * launch of `SM count` CTAs each) and keep their call counts on the device, so a launch has no call-dependent argument:
+ * a whole step (all_gather, forward, backward, reduce_scatter) may be captured into one CUDA graph and replayed.
  */
 typedef struct msda_peer_ctx {
     int32_t world, rank;
     const void *const *peer_shards;    /* host array [world]: device address of every rank's staging shard [B, chunk, H, D] */
     const void *const *peer_partials;  /* host array [world]: every rank's partial grad_img [B, world*chunk, H, D] (fp32) */
     uint32_t *const *peer_flags;       /* host array [world]: every rank's flag block, uint32 [4][world], zero-initialised */
-    uint32_t *counters;                /* this rank's 4 arrival counters (device), zero-initialised once */
+    uint32_t *counters;                /* this rank's 8 counter words (device), zero-initialised once */
 } msda_peer_ctx;
 
 int msda_peer_all_gather(void *full, const void *shard, const msda_peer_ctx *ctx, int64_t B, int64_t shard_bytes_per_image,
-                         uint32_t epoch_all_gather, uint32_t epoch_reduce_scatter_done, void *stream);
+                         void *stream);
 int msda_peer_reduce_scatter(void *grad_shard, const msda_peer_ctx *ctx, int64_t B, int64_t shard_floats_per_image,
-                             uint32_t epoch_reduce_scatter, void *stream);
+                             void *stream);
 
 #ifdef __cplusplus
 }

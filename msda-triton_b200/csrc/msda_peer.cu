@@ -10,7 +10,10 @@
 // All buffers the peers read live in symmetric memory (the host side allocates them with torch symmetric memory and
 // hands over the peers' device pointers).  Cross-rank ordering uses four flag rows per rank,
 //      flags[slot][src]   slot in {AG_READY, AG_DONE, RS_READY, RS_DONE},   written ONLY by rank `src`,
-// that carry monotonically increasing epochs (call counters kept by the host wrapper), so nothing is ever reset:
+// that carry monotonically increasing epochs, so nothing is ever reset.  The epochs are call counters kept ON THE DEVICE
+// (counters[4] = all-gathers issued, counters[5] = reduce-scatters issued; every kernel reads them at its start and its
+// last CTA bumps its own at the end), so a launch has no call-dependent argument and a whole training step -- all-gather,
+// forward, backward, reduce-scatter -- can be captured into ONE CUDA graph and replayed:
 //   all-gather e:   wait AG_DONE >= e-1 (peers finished reading my staging shard) and RS_DONE >= r (peers finished
 //                   reading my partial grad_img of the previous backward -- the coming backward overwrites it)
 //                   -> copy my shard into the staging buffer -> signal AG_READY = e -> wait for everybody's AG_READY
@@ -34,7 +37,7 @@ struct PeerArgs {
     const uint4 *shards[kMaxWorld];       // every rank's staging shard   [B, chunk, H, D]
     const float4 *partials[kMaxWorld];    // every rank's partial grad_img [B, world * chunk, H, D] fp32
     uint32_t *flags[kMaxWorld];           // every rank's flag block [4][world]
-    uint32_t *counters;                   // local, 4 words, zero between kernels
+    uint32_t *counters;                   // local: [0..2] CTA arrival counters (zero between kernels), [4] / [5] epochs
     int world, rank;
 };
 
@@ -65,26 +68,33 @@ __device__ void wait_all(const PeerArgs &a, int slot, uint32_t epoch) {
     __syncthreads();
 }
 // every CTA calls this after its part of the preceding phase; the last one to arrive publishes `epoch` in `slot` of
-// every rank's flag block (entry [slot][my rank])
-__device__ void arrive_and_signal(const PeerArgs &a, int counter, int slot, uint32_t epoch) {
+// every rank's flag block (entry [slot][my rank]) and, if asked to, records the epoch as this rank's call count
+__device__ void arrive_and_signal(const PeerArgs &a, int counter, int slot, uint32_t epoch, int bump = -1) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence_system();
         if (atomicAdd(a.counters + counter, 1u) == gridDim.x - 1) {
             a.counters[counter] = 0u;
+            if (bump >= 0) a.counters[bump] = epoch;    // every CTA of this launch has read the old value long ago
             __threadfence_system();
             for (int p = 0; p < a.world; ++p) st_release_sys(a.flags[p] + slot * a.world + a.rank, epoch);
         }
     }
+}
+__device__ __forceinline__ uint32_t ld_volatile(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 
 // n16: uint4 per image and rank (chunk * H * D * elem_size / 16)
 __global__ void __launch_bounds__(kThreads) peer_all_gather_kernel(const PeerArgs a, uint4 *__restrict__ full,
                                                                    const uint4 *__restrict__ shard_user,
                                                                    uint4 *__restrict__ staging, const long long B,
-                                                                   const long long n16, const uint32_t epoch_ag,
-                                                                   const uint32_t epoch_rs_done) {
+                                                                   const long long n16) {
     const long long tid = (long long)blockIdx.x * kThreads + threadIdx.x, stride = (long long)gridDim.x * kThreads;
+    const uint32_t epoch_ag = ld_volatile(a.counters + 4) + 1u;      // this is all-gather number ...
+    const uint32_t epoch_rs_done = ld_volatile(a.counters + 5);      // ... after that many reduce-scatters
     wait_all(a, AG_DONE, epoch_ag - 1u);
     wait_all(a, RS_DONE, epoch_rs_done);
     for (long long i = tid; i < B * n16; i += stride) {
@@ -117,14 +127,14 @@ __global__ void __launch_bounds__(kThreads) peer_all_gather_kernel(const PeerArg
             full[(b * a.world + p) * n16 + k] = ld_remote(src + i);
         }
     }
-    arrive_and_signal(a, 1, AG_DONE, epoch_ag);
+    arrive_and_signal(a, 1, AG_DONE, epoch_ag, 4);
 }
 
 // n4: float4 per image and rank
 __global__ void __launch_bounds__(kThreads) peer_reduce_scatter_kernel(const PeerArgs a, float4 *__restrict__ out,
-                                                                       const long long B, const long long n4,
-                                                                       const uint32_t epoch_rs) {
+                                                                       const long long B, const long long n4) {
     const long long tid = (long long)blockIdx.x * kThreads + threadIdx.x, stride = (long long)gridDim.x * kThreads;
+    const uint32_t epoch_rs = ld_volatile(a.counters + 5) + 1u;
     if (blockIdx.x == 0 && threadIdx.x == 0) {    // stream order: the backward that filled my partial has completed
         __threadfence_system();
         for (int p = 0; p < a.world; ++p) st_release_sys(a.flags[p] + RS_READY * a.world + a.rank, epoch_rs);
@@ -148,7 +158,7 @@ __global__ void __launch_bounds__(kThreads) peer_reduce_scatter_kernel(const Pee
             }
         out[i] = acc;
     }
-    arrive_and_signal(a, 2, RS_DONE, epoch_rs);
+    arrive_and_signal(a, 2, RS_DONE, epoch_rs, 5);
 }
 
 int fill(PeerArgs &k, const msda_peer_ctx *ctx) {
@@ -178,7 +188,7 @@ int sm_count_of_current_device() {
 extern "C" {
 
 int msda_peer_all_gather(void *full, const void *shard, const msda_peer_ctx *ctx, int64_t B, int64_t shard_bytes_per_image,
-                         uint32_t epoch_all_gather, uint32_t epoch_reduce_scatter_done, void *stream) {
+                         void *stream) {
     PeerArgs k;
     if (fill(k, ctx) != 0 || !full || !shard || B < 0 || shard_bytes_per_image < 0 || shard_bytes_per_image % 16 != 0)
         return MSDA_ERR_BAD_SHAPE;
@@ -188,12 +198,12 @@ int msda_peer_all_gather(void *full, const void *shard, const msda_peer_ctx *ctx
     uint4 *staging = const_cast<uint4 *>(k.shards[k.rank]);
     peer_all_gather_kernel<<<sms, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         k, static_cast<uint4 *>(full), static_cast<const uint4 *>(shard), staging, (long long)B,
-        (long long)(shard_bytes_per_image / 16), epoch_all_gather, epoch_reduce_scatter_done);
+        (long long)(shard_bytes_per_image / 16));
     return (int)cudaGetLastError();
 }
 
 int msda_peer_reduce_scatter(void *grad_shard, const msda_peer_ctx *ctx, int64_t B, int64_t shard_floats_per_image,
-                             uint32_t epoch_reduce_scatter, void *stream) {
+                             void *stream) {
     PeerArgs k;
     if (fill(k, ctx) != 0 || !grad_shard || B < 0 || shard_floats_per_image < 0 || shard_floats_per_image % 4 != 0)
         return MSDA_ERR_BAD_SHAPE;
@@ -201,7 +211,7 @@ int msda_peer_reduce_scatter(void *grad_shard, const msda_peer_ctx *ctx, int64_t
     const int sms = sm_count_of_current_device();
     if (sms <= 0) return (int)cudaErrorInvalidDevice;
     peer_reduce_scatter_kernel<<<sms, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        k, static_cast<float4 *>(grad_shard), (long long)B, (long long)(shard_floats_per_image / 4), epoch_reduce_scatter);
+        k, static_cast<float4 *>(grad_shard), (long long)B, (long long)(shard_floats_per_image / 4));
     return (int)cudaGetLastError();
 }
 

@@ -66,9 +66,9 @@ def _load() -> ctypes.CDLL:
     lib.msda_level_table.restype = ci
     lib.msda_level_table.argtypes = [vp, vp, i64, i64, vp]
     lib.msda_peer_all_gather.restype = ci
-    lib.msda_peer_all_gather.argtypes = [vp, vp, ctypes.POINTER(MsdaPeerCtx), i64, i64, ctypes.c_uint32, ctypes.c_uint32, vp]
+    lib.msda_peer_all_gather.argtypes = [vp, vp, ctypes.POINTER(MsdaPeerCtx), i64, i64, vp]
     lib.msda_peer_reduce_scatter.restype = ci
-    lib.msda_peer_reduce_scatter.argtypes = [vp, ctypes.POINTER(MsdaPeerCtx), i64, i64, ctypes.c_uint32, vp]
+    lib.msda_peer_reduce_scatter.argtypes = [vp, ctypes.POINTER(MsdaPeerCtx), i64, i64, vp]
     lib.msda_probe_gather.restype = ci
     lib.msda_probe_gather.argtypes = [vp, vp, i64, i64, ctypes.c_uint32, vp]
     lib.msda_probe_scatter.restype = ci

@@ -154,7 +154,9 @@ class PeerPixelExchange:
     Allocates, in symmetric memory: the staging pixel shard ``[B, chunk, H, D]`` the peers pull in the all-gather, this
     rank's partial ``grad_img`` ``[B, world * chunk, H, D]`` the peers pull in the reduce-scatter, and a flag block.
     The gathered pyramid itself is an ordinary tensor.  Create it once (collective call: every rank of ``group``) and
-    reuse it for every step; the ranks must issue the same sequence of :func:`peer_query_sharded_msda` calls."""
+    reuse it for every step; the ranks must issue the same sequence of :func:`peer_query_sharded_msda` calls.  The
+    collectives keep their call counts on the device, so a whole step can be captured into a CUDA graph
+    (``torch.cuda.graph``) and replayed -- every rank replaying the same number of times."""
 
     def __init__(self, batch: int, num_pixels: int, heads: int, channels: int, group=None,
                  device: Optional[torch.device] = None):
@@ -176,7 +178,7 @@ class PeerPixelExchange:
         self.flags = symm.empty((4 * 16,), dtype=torch.int32, device=dev)
         self.flags.zero_()
         self._handles = [symm.rendezvous(t, name) for t in (self.staging, self.partial, self.flags)]
-        self.counters = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.counters = torch.zeros(8, dtype=torch.int32, device=dev)   # CTA arrival counters + the two call counts
         self.full = torch.empty(self.shape_full, dtype=torch.float32, device=dev)
         arr = ctypes.c_void_p * self.world
         self._ptrs = [arr(*[int(p) for p in h.buffer_ptrs]) for h in self._handles]   # keep the host arrays alive
@@ -185,8 +187,6 @@ class PeerPixelExchange:
                                     ctypes.cast(self._ptrs[1], ctypes.POINTER(ctypes.c_void_p)),
                                     ctypes.cast(self._ptrs[2], ctypes.POINTER(ctypes.c_void_p)),
                                     ctypes.c_void_p(self.counters.data_ptr()))
-        self.n_all_gather = 0
-        self.n_reduce_scatter = 0
         torch.cuda.synchronize(dev)
         self._handles[2].barrier(channel=0)      # every rank's flags are zero before anybody signals
         torch.cuda.synchronize(dev)
@@ -195,11 +195,10 @@ class PeerPixelExchange:
         """[B, chunk, H, D] pixel shard of this rank -> the padded pyramid [B, world * chunk, H, D] (self.full)."""
         if tuple(shard.shape) != self.shape_shard or shard.dtype != torch.float32 or not shard.is_contiguous():
             raise ValueError(f"PeerPixelExchange.all_gather: expected a contiguous fp32 {self.shape_shard} shard")
-        self.n_all_gather += 1
         per_image = self.chunk * self.shape_shard[2] * self.shape_shard[3] * 4
         rc = _lib.get_lib().msda_peer_all_gather(
             self.full.data_ptr(), shard.data_ptr(), ctypes.byref(self.ctx), self.shape_shard[0], per_image,
-            self.n_all_gather, self.n_reduce_scatter, torch.cuda.current_stream(self.device).cuda_stream)
+            torch.cuda.current_stream(self.device).cuda_stream)
         if rc:
             _lib.check(rc, "msda_peer_all_gather")
         return self.full
@@ -208,10 +207,9 @@ class PeerPixelExchange:
         """Sum over the ranks of their partial grad_img (self.partial), this rank's pixel chunk: [B, chunk, H, D]."""
         if out is None:
             out = torch.empty(self.shape_shard, dtype=torch.float32, device=self.device)
-        self.n_reduce_scatter += 1
         per_image = self.chunk * self.shape_shard[2] * self.shape_shard[3]
         rc = _lib.get_lib().msda_peer_reduce_scatter(
-            out.data_ptr(), ctypes.byref(self.ctx), self.shape_shard[0], per_image, self.n_reduce_scatter,
+            out.data_ptr(), ctypes.byref(self.ctx), self.shape_shard[0], per_image,
             torch.cuda.current_stream(self.device).cuda_stream)
         if rc:
             _lib.check(rc, "msda_peer_reduce_scatter")

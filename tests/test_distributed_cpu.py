@@ -87,6 +87,30 @@ def _worker(rank, world, port, backend, device_kind, results):
                                                   wq2.detach(), pm, ac)
                 assert torch.equal(o, out_q)
             torch.cuda.synchronize()
+            # the whole peer step as one CUDA graph (device-side call counts): replays reproduce the eager results
+            sh3 = D.shard_pixels(img, rank, world).clone().requires_grad_(True)
+            pq3, wq3 = (D.shard_queries(t, rank, world).clone().requires_grad_(True) for t in (pts, aw))
+            go3 = D.shard_queries(go, rank, world).contiguous()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    D.peer_query_sharded_msda(ex, sh3, s, pq3, wq3, pm, ac).backward(go3)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            dist.barrier()
+            sh3.grad = pq3.grad = wq3.grad = None
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out_g = D.peer_query_sharded_msda(ex, sh3, s, pq3, wq3, pm, ac)
+                out_g.backward(go3)
+            for _ in range(3):
+                graph.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(out_g, out_q), "graph replay: forward differs"
+            assert torch.equal(pq3.grad, pq.grad) and torch.equal(wq3.grad, wq.grad)
+            torch.testing.assert_close(sh3.grad, want, rtol=1e-5, atol=1e-5)
+            del graph
         results[rank] = "ok"
     except Exception as ex:  # noqa: BLE001
         import traceback
