@@ -173,7 +173,8 @@ int msda_probe_scatter(float *buf, int64_t buf_rows, int64_t rows, uint32_t seed
  * symmetric memory by the host side (msda_triton/distributed.py: PeerPixelExchange), which passes every rank's device
  * pointers here.  fp32 pyramids; all sizes per image and rank.
  *
- *   msda_peer_all_gather      full[b, p*chunk .. (p+1)*chunk) <- rank p's pixel shard of image b, for every p
+ *   msda_peer_all_gather      every rank's pyramid[b, r*chunk .. (r+1)*chunk) <- this rank r's pixel shard of image b
+ *                             (pushed over NVLink); on return of the kernel this rank's pyramid holds all shards
  *   msda_peer_reduce_scatter  grad_shard[b, i] <- sum over ranks r (ascending) of partial_r[b, my_rank*chunk + i]
  *
  * Every rank of the group must issue the same sequence of calls.  The kernels spin on flags written by the peers (one
@@ -182,14 +183,13 @@ int msda_probe_scatter(float *buf, int64_t buf_rows, int64_t rows, uint32_t seed
  */
 typedef struct msda_peer_ctx {
     int32_t world, rank;
-    const void *const *peer_shards;    /* host array [world]: device address of every rank's staging shard [B, chunk, H, D] */
+    const void *const *peer_pyramids;  /* host array [world]: device address of every rank's gathered pyramid [B, world*chunk, H, D] */
     const void *const *peer_partials;  /* host array [world]: every rank's partial grad_img [B, world*chunk, H, D] (fp32) */
     uint32_t *const *peer_flags;       /* host array [world]: every rank's flag block, uint32 [4][world], zero-initialised */
     uint32_t *counters;                /* this rank's 8 counter words (device), zero-initialised once */
 } msda_peer_ctx;
 
-int msda_peer_all_gather(void *full, const void *shard, const msda_peer_ctx *ctx, int64_t B, int64_t shard_bytes_per_image,
-                         void *stream);
+int msda_peer_all_gather(const void *shard, const msda_peer_ctx *ctx, int64_t B, int64_t shard_bytes_per_image, void *stream);
 int msda_peer_reduce_scatter(void *grad_shard, const msda_peer_ctx *ctx, int64_t B, int64_t shard_floats_per_image,
                              void *stream);
 

@@ -7,17 +7,20 @@
 // produces a full-size PARTIAL grad_img on every rank whose sum has to end up pixel-sharded again
 // (/root/reference/src/msda_triton/kernels.py:549-553 is the only coupling between output rows).
 //
-// All buffers the peers read live in symmetric memory (the host side allocates them with torch symmetric memory and
+// All buffers the peers touch live in symmetric memory (the host side allocates them with torch symmetric memory and
 // hands over the peers' device pointers).  Cross-rank ordering uses four flag rows per rank,
 //      flags[slot][src]   slot in {AG_READY, AG_DONE, RS_READY, RS_DONE},   written ONLY by rank `src`,
 // that carry monotonically increasing epochs, so nothing is ever reset.  The epochs are call counters kept ON THE DEVICE
 // (counters[4] = all-gathers issued, counters[5] = reduce-scatters issued; every kernel reads them at its start and its
 // last CTA bumps its own at the end), so a launch has no call-dependent argument and a whole training step -- all-gather,
 // forward, backward, reduce-scatter -- can be captured into ONE CUDA graph and replayed:
-//   all-gather e:   wait AG_DONE >= e-1 (peers finished reading my staging shard) and RS_DONE >= r (peers finished
-//                   reading my partial grad_img of the previous backward -- the coming backward overwrites it)
-//                   -> copy my shard into the staging buffer -> signal AG_READY = e -> wait for everybody's AG_READY
-//                   -> pull the world-1 remote shards (own shard: local copy) -> signal AG_DONE = e
+//   all-gather e (PUSH): signal AG_READY = e ("I am in all-gather e: the kernels that read my pyramid in step e-1 have
+//                   completed -- stream order -- so you may write into it"); wait RS_DONE >= r (peers finished reading my
+//                   partial grad_img of the previous backward: the coming backward overwrites it); copy my shard into
+//                   my own pyramid; wait for everybody's AG_READY, then WRITE my shard into rows
+//                   [rank*chunk, (rank+1)*chunk) of every peer's pyramid (posted stores over NVLink; pulling the same
+//                   bytes with loads ran at 270-330 GB/s per GPU); signal AG_DONE = e ("my writes are complete"); wait for
+//                   everybody's AG_DONE: my pyramid is complete.
 //   reduce-scatter: signal RS_READY = r (stream order: my backward has completed) -> wait for everybody's RS_READY
 //                   -> out[b, i] = sum over ranks (fixed order 0..world-1: deterministic given the partials) of
 //                   partial_rank[b, my_rank * chunk + i] -> signal RS_DONE = r
@@ -34,7 +37,7 @@ enum { AG_READY = 0, AG_DONE = 1, RS_READY = 2, RS_DONE = 3 };
 constexpr int kMaxWorld = 16;
 
 struct PeerArgs {
-    const uint4 *shards[kMaxWorld];       // every rank's staging shard   [B, chunk, H, D]
+    uint4 *pyramids[kMaxWorld];           // every rank's gathered pyramid [B, world * chunk, H, D]
     const float4 *partials[kMaxWorld];    // every rank's partial grad_img [B, world * chunk, H, D] fp32
     uint32_t *flags[kMaxWorld];           // every rank's flag block [4][world]
     uint32_t *counters;                   // local: [0..2] CTA arrival counters (zero between kernels), [4] / [5] epochs
@@ -87,47 +90,40 @@ __device__ __forceinline__ uint32_t ld_volatile(const uint32_t *p) {
     return v;
 }
 
+__device__ __forceinline__ void st_remote(uint4 *p, const uint4 v) {   // posted store into a peer's memory
+    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 // n16: uint4 per image and rank (chunk * H * D * elem_size / 16)
-__global__ void __launch_bounds__(kThreads) peer_all_gather_kernel(const PeerArgs a, uint4 *__restrict__ full,
-                                                                   const uint4 *__restrict__ shard_user,
-                                                                   uint4 *__restrict__ staging, const long long B,
-                                                                   const long long n16) {
+__global__ void __launch_bounds__(kThreads) peer_all_gather_kernel(const PeerArgs a, const uint4 *__restrict__ shard,
+                                                                   const long long B, const long long n16) {
     const long long tid = (long long)blockIdx.x * kThreads + threadIdx.x, stride = (long long)gridDim.x * kThreads;
     const uint32_t epoch_ag = ld_volatile(a.counters + 4) + 1u;      // this is all-gather number ...
     const uint32_t epoch_rs_done = ld_volatile(a.counters + 5);      // ... after that many reduce-scatters
-    wait_all(a, AG_DONE, epoch_ag - 1u);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {   // stream order: whatever read my pyramid in the previous step is done
+        __threadfence_system();
+        for (int p = 0; p < a.world; ++p) st_release_sys(a.flags[p] + AG_READY * a.world + a.rank, epoch_ag);
+    }
     wait_all(a, RS_DONE, epoch_rs_done);
-    for (long long i = tid; i < B * n16; i += stride) {
-        const uint4 v = __ldg(shard_user + i);
-        staging[i] = v;
+    const long long per_rank = B * n16;
+    uint4 *__restrict__ own = a.pyramids[a.rank];
+    for (long long i = tid; i < per_rank; i += stride) {        // my own part of my own pyramid
         const long long b = i / n16, k = i - b * n16;
-        full[(b * a.world + a.rank) * n16 + k] = v;          // my own part of the pyramid
+        own[(b * a.world + a.rank) * n16 + k] = __ldg(shard + i);
     }
-    arrive_and_signal(a, 0, AG_READY, epoch_ag);
+    // my shard into every peer's pyramid: one flat index space over (peer, element) so that all world-1 links carry
+    // traffic at once and a thread has several independent stores in flight (a shard is only ~5 elements per thread;
+    // one phase per peer cost 7 flag waits and 7 short bursts: 0.152 ms at 8 GPUs); the peer order is rotated by the rank
     wait_all(a, AG_READY, epoch_ag);
-    // remote parts: peer p's shard of image b -> rows [p * chunk, (p+1) * chunk) of image b.  Peers are visited starting
-    // with my right-hand neighbour so that at any moment the ranks read from different peers.
-    const long long per_peer = B * n16;
-    for (int d = 1; d < a.world; ++d) {
-        const int p = (a.rank + d) % a.world;
-        const uint4 *__restrict__ src = a.shards[p];
-        long long i = tid;
-        for (; i + 7 * stride < per_peer; i += 8 * stride) {   // eight loads in flight per thread
-            uint4 v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = ld_remote(src + i + u * stride);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const long long j = i + u * stride, b = j / n16, k = j - b * n16;
-                full[(b * a.world + p) * n16 + k] = v[u];
-            }
-        }
-        for (; i < per_peer; i += stride) {
-            const long long b = i / n16, k = i - b * n16;
-            full[(b * a.world + p) * n16 + k] = ld_remote(src + i);
-        }
+    const long long remote = per_rank * (a.world - 1);
+    for (long long i = tid; i < remote; i += stride) {
+        const int d = (int)(i / per_rank);
+        const long long e = i - (long long)d * per_rank;
+        const int p = (a.rank + 1 + d) % a.world;
+        const long long b = e / n16, k = e - b * n16;
+        st_remote(a.pyramids[p] + (b * a.world + a.rank) * n16 + k, __ldg(shard + e));
     }
-    arrive_and_signal(a, 1, AG_DONE, epoch_ag, 4);
+    arrive_and_signal(a, 1, AG_DONE, epoch_ag, 4);    // fence + "my writes have landed"
+    wait_all(a, AG_DONE, epoch_ag);                   // everybody's writes into MY pyramid have landed
 }
 
 // n4: float4 per image and rank
@@ -163,15 +159,15 @@ __global__ void __launch_bounds__(kThreads) peer_reduce_scatter_kernel(const Pee
 
 int fill(PeerArgs &k, const msda_peer_ctx *ctx) {
     if (!ctx || ctx->world < 1 || ctx->world > kMaxWorld || ctx->rank < 0 || ctx->rank >= ctx->world) return -1;
-    if (!ctx->peer_shards || !ctx->peer_partials || !ctx->peer_flags || !ctx->counters) return -1;
+    if (!ctx->peer_pyramids || !ctx->peer_partials || !ctx->peer_flags || !ctx->counters) return -1;
     k.world = ctx->world;
     k.rank = ctx->rank;
     k.counters = ctx->counters;
     for (int r = 0; r < ctx->world; ++r) {
-        k.shards[r] = static_cast<const uint4 *>(ctx->peer_shards[r]);
+        k.pyramids[r] = static_cast<uint4 *>(const_cast<void *>(ctx->peer_pyramids[r]));
         k.partials[r] = static_cast<const float4 *>(ctx->peer_partials[r]);
         k.flags[r] = ctx->peer_flags[r];
-        if (!k.shards[r] || !k.partials[r] || !k.flags[r]) return -1;
+        if (!k.pyramids[r] || !k.partials[r] || !k.flags[r]) return -1;
     }
     return 0;
 }
@@ -187,18 +183,15 @@ int sm_count_of_current_device() {
 
 extern "C" {
 
-int msda_peer_all_gather(void *full, const void *shard, const msda_peer_ctx *ctx, int64_t B, int64_t shard_bytes_per_image,
-                         void *stream) {
+int msda_peer_all_gather(const void *shard, const msda_peer_ctx *ctx, int64_t B, int64_t shard_bytes_per_image, void *stream) {
     PeerArgs k;
-    if (fill(k, ctx) != 0 || !full || !shard || B < 0 || shard_bytes_per_image < 0 || shard_bytes_per_image % 16 != 0)
+    if (fill(k, ctx) != 0 || !shard || B < 0 || shard_bytes_per_image < 0 || shard_bytes_per_image % 16 != 0)
         return MSDA_ERR_BAD_SHAPE;
-    if (((uintptr_t)full | (uintptr_t)shard) & 15u) return MSDA_ERR_BAD_SHAPE;
+    if ((uintptr_t)shard & 15u) return MSDA_ERR_BAD_SHAPE;
     const int sms = sm_count_of_current_device();
     if (sms <= 0) return (int)cudaErrorInvalidDevice;
-    uint4 *staging = const_cast<uint4 *>(k.shards[k.rank]);
     peer_all_gather_kernel<<<sms, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        k, static_cast<uint4 *>(full), static_cast<const uint4 *>(shard), staging, (long long)B,
-        (long long)(shard_bytes_per_image / 16));
+        k, static_cast<const uint4 *>(shard), (long long)B, (long long)(shard_bytes_per_image / 16));
     return (int)cudaGetLastError();
 }
 

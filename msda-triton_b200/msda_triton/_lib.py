@@ -22,7 +22,7 @@ BWD_NEED_IMG, BWD_NEED_POINTS, BWD_NEED_WEIGHTS, BWD_DETERMINISTIC, BWD_NEED_REF
 class MsdaPeerCtx(ctypes.Structure):
     """struct msda_peer_ctx (include/msda_b200.h): every rank's device pointers, as host arrays."""
     _fields_ = [("world", ctypes.c_int32), ("rank", ctypes.c_int32),
-                ("peer_shards", ctypes.POINTER(ctypes.c_void_p)), ("peer_partials", ctypes.POINTER(ctypes.c_void_p)),
+                ("peer_pyramids", ctypes.POINTER(ctypes.c_void_p)), ("peer_partials", ctypes.POINTER(ctypes.c_void_p)),
                 ("peer_flags", ctypes.POINTER(ctypes.c_void_p)), ("counters", ctypes.c_void_p)]
 
 
@@ -66,7 +66,7 @@ def _load() -> ctypes.CDLL:
     lib.msda_level_table.restype = ci
     lib.msda_level_table.argtypes = [vp, vp, i64, i64, vp]
     lib.msda_peer_all_gather.restype = ci
-    lib.msda_peer_all_gather.argtypes = [vp, vp, ctypes.POINTER(MsdaPeerCtx), i64, i64, vp]
+    lib.msda_peer_all_gather.argtypes = [vp, ctypes.POINTER(MsdaPeerCtx), i64, i64, vp]
     lib.msda_peer_reduce_scatter.restype = ci
     lib.msda_peer_reduce_scatter.argtypes = [vp, ctypes.POINTER(MsdaPeerCtx), i64, i64, vp]
     lib.msda_probe_gather.restype = ci

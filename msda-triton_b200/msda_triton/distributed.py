@@ -151,9 +151,9 @@ def all_reduce_grad_img_(grad_img: torch.Tensor, group=None) -> torch.Tensor:
 class PeerPixelExchange:
     """Buffers and flags for query-sharded MSDA over peer memory, for a fixed problem size (fp32).
 
-    Allocates, in symmetric memory: the staging pixel shard ``[B, chunk, H, D]`` the peers pull in the all-gather, this
-    rank's partial ``grad_img`` ``[B, world * chunk, H, D]`` the peers pull in the reduce-scatter, and a flag block.
-    The gathered pyramid itself is an ordinary tensor.  Create it once (collective call: every rank of ``group``) and
+    Allocates, in symmetric memory: the gathered pyramid ``[B, world * chunk, H, D]`` the peers PUSH their shards into
+    in the all-gather, this rank's partial ``grad_img`` (same shape) the peers pull from in the reduce-scatter, and a
+    flag block.  Create it once (collective call: every rank of ``group``) and
     reuse it for every step; the ranks must issue the same sequence of :func:`peer_query_sharded_msda` calls.  The
     collectives keep their call counts on the device, so a whole step can be captured into a CUDA graph
     (``torch.cuda.graph``) and replayed -- every rank replaying the same number of times."""
@@ -173,13 +173,12 @@ class PeerPixelExchange:
         if (self.chunk * heads * channels * 4) % 16:
             raise ValueError("PeerPixelExchange: a pixel chunk must be a multiple of 16 bytes")
         name = self.group.group_name
-        self.staging = symm.empty(self.shape_shard, dtype=torch.float32, device=dev)
+        self.full = symm.empty(self.shape_full, dtype=torch.float32, device=dev)
         self.partial = symm.empty(self.shape_full, dtype=torch.float32, device=dev)
         self.flags = symm.empty((4 * 16,), dtype=torch.int32, device=dev)
         self.flags.zero_()
-        self._handles = [symm.rendezvous(t, name) for t in (self.staging, self.partial, self.flags)]
+        self._handles = [symm.rendezvous(t, name) for t in (self.full, self.partial, self.flags)]
         self.counters = torch.zeros(8, dtype=torch.int32, device=dev)   # CTA arrival counters + the two call counts
-        self.full = torch.empty(self.shape_full, dtype=torch.float32, device=dev)
         arr = ctypes.c_void_p * self.world
         self._ptrs = [arr(*[int(p) for p in h.buffer_ptrs]) for h in self._handles]   # keep the host arrays alive
         self.ctx = _lib.MsdaPeerCtx(self.world, self.rank,
@@ -197,7 +196,7 @@ class PeerPixelExchange:
             raise ValueError(f"PeerPixelExchange.all_gather: expected a contiguous fp32 {self.shape_shard} shard")
         per_image = self.chunk * self.shape_shard[2] * self.shape_shard[3] * 4
         rc = _lib.get_lib().msda_peer_all_gather(
-            self.full.data_ptr(), shard.data_ptr(), ctypes.byref(self.ctx), self.shape_shard[0], per_image,
+            shard.data_ptr(), ctypes.byref(self.ctx), self.shape_shard[0], per_image,
             torch.cuda.current_stream(self.device).cuda_stream)
         if rc:
             _lib.check(rc, "msda_peer_all_gather")

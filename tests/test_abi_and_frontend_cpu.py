@@ -43,7 +43,7 @@ def test_peer_entry_points_validate_without_a_gpu(libpath):
     from msda_triton import _lib
     lib = _lib.get_lib()
     ctx = _lib.MsdaPeerCtx(0, 0, None, None, None, None)          # world = 0
-    assert lib.msda_peer_all_gather(None, None, ctypes.byref(ctx), 1, 16, None) < 0
+    assert lib.msda_peer_all_gather(None, ctypes.byref(ctx), 1, 16, None) < 0
     assert lib.msda_peer_reduce_scatter(None, ctypes.byref(ctx), 1, 4, None) < 0
 
 
