@@ -345,10 +345,12 @@ __device__ __forceinline__ void derive_operands(const KernelArgs &a, const Level
 // Deterministic backward by exact row adds (msda_bwd_detq.cu): the quantum of (b, h, level) entry `idx`.
 //   R = slmax[idx]: the largest row counter of the slice-level; a row's counter is the sum of t_i = ceil(|c_i| / U) + 1 over
 //   its contributions c_i, U = amax / 4096, hence  sum |c_i| <= U (R - n)  for a row with n contributions.
-//   A value c rounded to a multiple of q moves by at most q/2, so with q <= 2U:  sum |c'_i| <= U (R - n) + n q/2 <= U R.
-//   q = 2^(ilogb(U R) + 1 - 24)  >  U R 2^-24  keeps every partial sum of every row, in any order, an integer multiple of q
-//   below 2^24 q: exactly representable, no add ever rounds.  (q <= 2U needs R <= 2^24; rows beyond that -- 10^5 and
-//   more contributions -- use the cruder  sum |c'| <= 2 sum |c|  and one more bit of head room.)
+//   The kernel rounds c to c' = a multiple of q with |c' - c| <= q/2 (<= q for the at most three contributions per row
+//   that exceed 2^22 q, where fp32 spacing is 2q).  With q <= U/2, which R <= 2^22 guarantees:
+//       sum |c'_i| <= U (R - n) + n q/2 + 3 q/2 <= U R        (n >= 3; two addends commute whatever they are)
+//   and  q = 2^(ilogb(U R) + 1 - 24) > U R 2^-24  keeps every partial sum of every row, in any order, an integer multiple
+//   of q below 2^24 q: exactly representable, no add ever rounds.  Rows beyond R = 2^22 -- 10^4 and more contributions
+//   of full size -- use the cruder  sum |c'| <= 2 sum |c|  and one more bit of head room.
 // Returns 0 ("do not quantise") when nothing lands on the slice-level or the inputs are not finite.
 __device__ __forceinline__ float row_quantum(const KernelArgs &a, int idx) {
     const unsigned long long r = a.q_slmax[idx];
@@ -356,7 +358,7 @@ __device__ __forceinline__ float row_quantum(const KernelArgs &a, int idx) {
     if (r == 0ull || !(amax > 0.0f) || !(amax < 3.0e38f)) return 0.0f;
     const float bound = (float)r * (amax * (1.0f / 4096.0f));
     if (!(bound > 1.0e-30f) || !(bound < 1.0e30f)) return 0.0f;
-    return scalbnf(1.0f, ilogbf(bound) + (r <= (1ull << 24) ? 1 : 2) - 24);
+    return scalbnf(1.0f, ilogbf(bound) + (r <= (1ull << 22) ? 1 : 2) - 24);
 }
 
 // Read-only gather of one lane's slice of a corner row (16 bytes, or 8 bytes for the 16-bit-storage backward that runs
