@@ -47,6 +47,10 @@ WORKLOADS = {
     # encoder self-attention with realistic locality: query q sits on pixel q of the pyramid and samples
     # N(0, 2 px) around its own normalised position on every level (SURVEY.md 8d, M2 "encoder-realistic" variant)
     "detr_encoder_local_zeros": (2, 22223, 8, 32, DETR_PYRAMID, 4, "zeros", False),
+    # encoder self-attention of a freshly initialised Deformable-DETR: query q sits on pixel q and every query uses the
+    # SAME offsets -- point k of head h at (k+1) pixels (of each level) along direction 2 pi h / H, the model's bias
+    # initialisation -- plus N(0, 0.1 px) of per-query variation: neighbouring queries share cells on the coarser levels
+    "detr_encoder_init_zeros": (2, 22223, 8, 32, DETR_PYRAMID, 4, "zeros", False),
 }
 HEADLINE = "bench_q10k_border"
 METRIC = "MSDA fwd+bwd throughput, 10k-query benchmark shape (fp32)"
@@ -84,7 +88,22 @@ def make_inputs(name, seed, device="cpu", pin=False):
     L = len(pyr)
     npix = sum(h * w for h, w in pyr)
     pts = torch.rand(B, Q, H, L, K, 2, generator=g)
-    if "local" in name:
+    if "init" in name:
+        import math
+        centres = []
+        for (h, w) in pyr:
+            ys, xs = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+            centres.append(torch.stack(((xs.reshape(-1) + 0.5) / w, (ys.reshape(-1) + 0.5) / h), dim=-1))
+        ref = torch.cat(centres)[:Q]                                                     # [Q, 2]
+        wh = torch.tensor([[w, h] for (h, w) in pyr], dtype=torch.float32)               # per level (w, h)
+        theta = torch.arange(H, dtype=torch.float32) * (2.0 * math.pi / H)
+        direction = torch.stack((theta.cos(), theta.sin()), -1)
+        direction = direction / direction.abs().max(-1, keepdim=True).values             # [H, 2], as the model's init
+        steps = torch.arange(1, K + 1, dtype=torch.float32)                              # point k: (k + 1) pixels
+        off_px = direction[:, None, None, :] * steps[None, None, :, None]                # [H, 1, K, 2]
+        off_px = off_px + torch.randn(B, Q, H, L, K, 2, generator=g) * 0.1
+        pts = ref[None, :, None, None, None, :] + off_px / wh[None, None, None, :, None, :]
+    elif "local" in name:
         # reference point = centre of the query's own pixel (queries enumerate the pyramid in storage order)
         centres = []
         for (h, w) in pyr:

@@ -42,10 +42,24 @@ template <int VEC, int LANES> __device__ __forceinline__ void red_add_row(float 
 // QUANT: deterministic mode (msda_bwd_detq.cu).  Every value added to grad_img is first rounded to a multiple of a
 // power-of-two quantum q chosen per (b, h, level) such that NO partial sum of a row can exceed 2^24 q: all the fp32 adds
 // of the row are then exact, hence associative, and the relaxed atomics give the same bits in any order.
+// AGG: warp-level aggregation of the row adds of NEIGHBOURING QUERIES.  A warp tile holds four consecutive queries of one
+// (b,h); when two of them (lane groups g and g^1) put a sampling point into the same pixel cell with the same corner
+// validity -- encoder self-attention: query q sits on pixel q, so adjacent queries hit the same cell on every level
+// coarser than their own -- the even group adds BOTH contributions with one row add and the odd group adds nothing.
+// The groups do not exchange the 16 products of a point (as many LSU wavefronts as the adds saved) but the three
+// numbers they derive from: (attention weight, dx, dy) of the partner's point, plus the partner's grad_out slice once
+// per tile.  Finding the pairs costs 4 shuffles + 2 votes per TILE (every lane compares the taps of its own two points
+// with the partner group's); tiles without a pair run the plain path.
+// MEASURED (B200, DETR encoder B=2): it loses.  Uniform random points (no pairs): 0.543 -> 0.582 ms, the price of the
+// check and of the extra live registers; freshly-initialised-DETR points (identical offsets for all queries: ~53 % of the
+// point slots pair, 26 % fewer row-add sectors): 0.498 -> 0.568 ms.  A red.v4 warp instruction with half of its lane
+// groups predicated off costs the LSU what a full one costs -- only removing whole instructions helps, and a point's
+// four corner adds are issued for the warp's four units together.  OPT-IN: MSDA_B200_BWD_AGG=1 (tests keep it correct).
 template <typename T, int LANES, int LK, bool BORDER, int NB, int THREADS, bool FUSED, int VEC, bool PADDED,
-          bool SPLIT, bool QUANT = false>
+          bool SPLIT, bool QUANT = false, bool AGG = false>
 __global__ void __launch_bounds__(THREADS, 1)
     msda_bwd_tiled_kernel(const KernelArgs a, const WaveSchedule ws, const int subs_arg) {
+    static_assert(!AGG || (LANES == 8 && VEC == 4 && !PADDED && !SPLIT), "pair aggregation: four 8-lane groups per warp");
     using Cfg = TiledCfg<T, LANES, LK>;
     constexpr int G = Cfg::G, PPL = Cfg::PPL;
     using Raw = typename RawSlice<VEC * (int)sizeof(T)>::type;
@@ -116,6 +130,29 @@ __global__ void __launch_bounds__(THREADS, 1)
             if constexpr (QUANT) quantum[pp] = row_quantum(a, (tile / tiles_per_bh) * a.L + lvl);
         }
 
+        // AGG: bit (8 g + jj) of pair_mask[pp] = point jj*PPL+pp of group g's unit shares its cell with the partner
+        // group's (g ^ 1) same point; partner_go = the partner unit's grad_out slice of this lane's channels
+        unsigned pair_mask[AGG ? PPL : 1];
+        float partner_go[AGG ? VEC : 1];
+        if constexpr (AGG) {
+            unsigned any_pair = 0u;
+#pragma unroll
+            for (int pp = 0; pp < PPL; ++pp) {
+                // padding queries (and launches without grad_img) never pair: bit 31 of the pack is otherwise unused
+                const unsigned key = (live && need_img) ? tap[pp].pack : (0x80000000u | (unsigned)lane);
+                const unsigned p_off = __shfl_xor_sync(0xffffffffu, tap[pp].off, LANES);
+                const unsigned p_key = __shfl_xor_sync(0xffffffffu, key, LANES);
+                pair_mask[pp] = __ballot_sync(0xffffffffu, p_off == tap[pp].off && p_key == key);
+                any_pair |= pair_mask[pp];
+            }
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) partner_go[e] = 0.0f;
+            if (any_pair) {   // warp-uniform
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) partner_go[e] = __shfl_xor_sync(0xffffffffu, go[e], LANES);
+            }
+        }
+
         // part[(jj*PPL + pp)*3 + {0,1,2}] : point jj*PPL+pp  ->  {grad weight, d/dx, d/dy} partial over my channels
         float part[3 * LK];
 
@@ -126,11 +163,27 @@ __global__ void __launch_bounds__(THREADS, 1)
                 Raw raw[NB][4];
                 float fx[NB], fy[NB], fw[NB];
                 float fq[QUANT ? NB : 1];
+                float pw[AGG ? NB : 1], pdx[AGG ? NB : 1], pdy[AGG ? NB : 1];   // AGG: the partner's point
+                bool add_partner[AGG ? NB : 1], leave_to_partner[AGG ? NB : 1];
                 unsigned o[NB][4];
                 unsigned msk[NB];
 #pragma unroll
                 for (int n = 0; n < NB; ++n) {
                     const int src = jj0 + n;
+                    if constexpr (AGG) {
+                        add_partner[n] = leave_to_partner[n] = false;
+                        pw[n] = pdx[n] = pdy[n] = 0.0f;
+                        const unsigned groups = (pair_mask[pp] >> src) & 0x01010101u;   // bit 8g: group g pairs on this point
+                        if (groups) {   // warp-uniform
+                            const int partner_lane = ((g ^ 1) * LANES) + src;
+                            pw[n] = __shfl_sync(0xffffffffu, op.wa[pp], partner_lane);
+                            pdx[n] = __shfl_sync(0xffffffffu, tap[pp].dx, partner_lane);
+                            pdy[n] = __shfl_sync(0xffffffffu, tap[pp].dy, partner_lane);
+                            const bool paired = (groups >> (8 * g)) & 1u;
+                            add_partner[n] = paired && !(g & 1);
+                            leave_to_partner[n] = paired && (g & 1);
+                        }
+                    }
                     // dead slots of a padded instantiation carry point (0,0) with weight 0: they are gathered like any
                     // other (one in-range row, L1 hits) so that the NB x 4 loads stay one branch-free batch, and only
                     // their row adds are skipped
@@ -158,6 +211,14 @@ __global__ void __launch_bounds__(THREADS, 1)
                     bw[3] = dy * dx;
                     bw[2] = dy - bw[3];
                     float d[4];
+                    float pbw[AGG ? 4 : 1];   // AGG: the partner's corner weights (attention x bilinear)
+                    if constexpr (AGG) {
+                        const float b1 = (1.0f - pdy[n]) * pdx[n], b3 = pdy[n] * pdx[n];
+                        pbw[0] = pw[n] * ((1.0f - pdy[n]) - b1);
+                        pbw[1] = pw[n] * b1;
+                        pbw[2] = pw[n] * (pdy[n] - b3);
+                        pbw[3] = pw[n] * b3;
+                    }
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         float v[VEC];
@@ -169,7 +230,14 @@ __global__ void __launch_bounds__(THREADS, 1)
                         if (need_img) {
                             const float s = fw[n] * bw[c];
                             float gv[VEC];
-                            if constexpr (!QUANT) {
+                            if constexpr (AGG) {
+#pragma unroll
+                                for (int e = 0; e < VEC; ++e) gv[e] = go[e] * s;
+                                if (add_partner[n]) {
+#pragma unroll
+                                    for (int e = 0; e < VEC; ++e) gv[e] = fmaf(partner_go[e], pbw[c], gv[e]);
+                                }
+                            } else if constexpr (!QUANT) {
 #pragma unroll
                                 for (int e = 0; e < VEC; ++e) gv[e] = go[e] * s;
                             } else {
@@ -187,7 +255,9 @@ __global__ void __launch_bounds__(THREADS, 1)
                                 }
                             }
                             float *dst = reinterpret_cast<float *>(gimg_base + (size_t)o[n][c] * kAccScale);
-                            if (live && alive && (BORDER || ((msk[n] >> c) & 1u))) red_add_row<VEC, LANES>(dst, gv);
+                            bool add = live && alive && (BORDER || ((msk[n] >> c) & 1u));
+                            if constexpr (AGG) add = add && !leave_to_partner[n];
+                            if (add) red_add_row<VEC, LANES>(dst, gv);
                         }
                     }
                     const int pidx = (jj0 + n) * PPL + pp;
@@ -317,7 +387,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 
 
 template <typename T, int LANES, int LK, bool FUSED = false, int VEC = 16 / (int)sizeof(T), bool PADDED = false,
-          bool SPLIT = false, bool QUANT = false>
+          bool SPLIT = false, bool QUANT = false, bool AGG = false>
 static cudaError_t launch_tiled_t(const KernelArgs &a, int sm_count, cudaStream_t st, int subs = 1) {
     constexpr int THREADS = 512, NB = 2;
     constexpr int G = TiledCfg<T, LANES, LK>::G;
@@ -339,10 +409,10 @@ static cudaError_t launch_tiled_t(const KernelArgs &a, int sm_count, cudaStream_
         if (e != cudaSuccess) return e;
     }
     if (a.border)
-        msda_bwd_tiled_kernel<T, LANES, LK, true, NB, THREADS, FUSED, VEC, PADDED, SPLIT, QUANT>
+        msda_bwd_tiled_kernel<T, LANES, LK, true, NB, THREADS, FUSED, VEC, PADDED, SPLIT, QUANT, AGG>
             <<<grid, THREADS, 0, st>>>(a, ws, subs);
     else
-        msda_bwd_tiled_kernel<T, LANES, LK, false, NB, THREADS, FUSED, VEC, PADDED, SPLIT, QUANT>
+        msda_bwd_tiled_kernel<T, LANES, LK, false, NB, THREADS, FUSED, VEC, PADDED, SPLIT, QUANT, AGG>
             <<<grid, THREADS, 0, st>>>(a, ws, subs);
     return cudaGetLastError();
 }
@@ -465,6 +535,9 @@ cudaError_t launch_backward_tiled(const KernelArgs &a, int dtype, int sm_count, 
                 const cudaError_t e = launch_backward_tmem(a, dtype, sm_count, st);
                 if (e != cudaErrorNotSupported) return e;
             }
+            // opt-in experiment (measured slower, see AGG above): pair aggregation of neighbouring queries' row adds
+            if (tuning().bwd_agg > 0 && (a.flags & kNeedImg))
+                return launch_tiled_t<float, 8, 16, false, 4, false, false, false, true>(a, sm_count, st);
             return launch_tiled_t<float, 8, 16>(a, sm_count, st);
         }
         if (a.D == 64) return launch_tiled_t<float, 16, 16>(a, sm_count, st);

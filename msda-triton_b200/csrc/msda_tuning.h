@@ -18,6 +18,7 @@ struct Tuning {
     int tmem_levels = 2;       // MSDA_B200_TMEM_LEVELS=0|1|2  : at most this many of the coarsest levels go to tensor memory
     int l1_keep_kb = 100;      // MSDA_B200_L1_KEEP_KB=n       : pyramid KB per (b,h) slice the forward keeps in L1; finer levels
                                //                                are gathered with no-allocate loads (-1: never)
+    int bwd_agg = -1;          // MSDA_B200_BWD_AGG=0|1        : pair aggregation of neighbouring queries' row adds (experiment, default off)
     int det_variant = -1;      // MSDA_B200_DET_VARIANT=0|1    : deterministic grad_img: 0 = radix sort, 1 = slice binning
 };
 
