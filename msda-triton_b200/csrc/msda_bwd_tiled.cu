@@ -52,9 +52,11 @@ template <int VEC, int LANES> __device__ __forceinline__ void red_add_row(float 
 // with the partner group's); tiles without a pair run the plain path.
 // MEASURED (B200, DETR encoder B=2): it loses.  Uniform random points (no pairs): 0.543 -> 0.582 ms, the price of the
 // check and of the extra live registers; freshly-initialised-DETR points (identical offsets for all queries: ~53 % of the
-// point slots pair, 26 % fewer row-add sectors): 0.498 -> 0.568 ms.  A red.v4 warp instruction with half of its lane
-// groups predicated off costs the LSU what a full one costs -- only removing whole instructions helps, and a point's
-// four corner adds are issued for the warp's four units together.  OPT-IN: MSDA_B200_BWD_AGG=1 (tests keep it correct).
+// point slots pair, 26 % fewer row adds): 0.498 -> 0.568 ms.  A row add costs the SM 5.8 clk per 128-byte row whatever
+// the shape of the instruction that carries it (scripts/micro/red_shapes.cu: lane groups predicated off, adjacent rows,
+// v2 / scalar forms all give 6.2-6.4 TB/s), so a paired point saves 4 rows = 23 clk -- and pays three full-warp shuffles
+// through the same saturated LSU plus the partner's weight arithmetic, which is no cheaper.
+// OPT-IN: MSDA_B200_BWD_AGG=1 (tests keep it correct).
 template <typename T, int LANES, int LK, bool BORDER, int NB, int THREADS, bool FUSED, int VEC, bool PADDED,
           bool SPLIT, bool QUANT = false, bool AGG = false>
 __global__ void __launch_bounds__(THREADS, 1)
