@@ -32,6 +32,9 @@ void read_env() {
     t.tmem_warps = env_int("MSDA_B200_TMEM_WARPS", 15);
     t.l1_keep_kb = env_int("MSDA_B200_L1_KEEP_KB", 100);
     t.bwd_agg = env_int("MSDA_B200_BWD_AGG", -1);
+    t.bwd_dense = env_int("MSDA_B200_BWD_DENSE", -1);
+    t.dense_prefetch = env_int("MSDA_B200_DENSE_PF", 3);
+    t.bwd_shape = env_int("MSDA_B200_BWD_SHAPE", -1);
     t.det_variant = env_int("MSDA_B200_DET_VARIANT", -1);
     g_tuning = t;
 }

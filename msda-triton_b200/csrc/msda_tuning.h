@@ -19,6 +19,10 @@ struct Tuning {
     int l1_keep_kb = 100;      // MSDA_B200_L1_KEEP_KB=n       : pyramid KB per (b,h) slice the forward keeps in L1; finer levels
                                //                                are gathered with no-allocate loads (-1: never)
     int bwd_agg = -1;          // MSDA_B200_BWD_AGG=0|1        : pair aggregation of neighbouring queries' row adds (experiment, default off)
+    int bwd_dense = -1;        // MSDA_B200_BWD_DENSE=n        : owner warps of the dense-level backward (experiment, default off)
+    int dense_prefetch = 3;    // MSDA_B200_DENSE_PF=3|4       : units an owner warp keeps in flight
+    int bwd_shape = -1;        // MSDA_B200_BWD_SHAPE=0..5     : fp32 backward launch shape: 16 warps x 128 regs | 12 x 168 | experiments
+                               //                                (default: 12 x 168 for problems with many warp tiles per warp)
     int det_variant = -1;      // MSDA_B200_DET_VARIANT=0|1    : deterministic grad_img: 0 = radix sort, 1 = slice binning
 };
 
