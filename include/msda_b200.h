@@ -65,7 +65,11 @@ enum msda_bwd_flags {
     MSDA_BWD_NEED_WEIGHTS = 4,  /* produce grad_attention_weights (ctx.needs_input_grad[3]) */
     MSDA_BWD_NEED_ALL = 7,
     MSDA_BWD_DETERMINISTIC = 8, /* grad_img by sorted-segment reduction instead of atomics (bit-reproducible) */
-    MSDA_BWD_NEED_REF = 16      /* msda_module_backward only: produce grad_reference_points */
+    MSDA_BWD_NEED_REF = 16,     /* msda_module_backward only: produce grad_reference_points */
+    MSDA_BWD_VALUE_COLSUM = 32  /* msda_module_backward only, fp16/bf16 storage: also leave sum over (b, pixel) of
+                                   grad_value[b, pixel, h, c] -- the bias gradient of the projection that produced
+                                   `value` (frontend.py:259, img_input_proj) -- as H*D floats at
+                                   workspace + msda_module_colsum_offset(prob); see msda_module_backward */
 };
 
 enum msda_error {
@@ -144,8 +148,15 @@ int msda_backward(void *grad_img, void *grad_points, void *grad_weights, const v
  * Backward flags: MSDA_BWD_NEED_IMG -> grad_value, NEED_POINTS|NEED_WEIGHTS -> grad_proj, NEED_REF -> grad_ref.
  * grad_ref is an fp32 [B, Q, ref_dim] buffer regardless of the storage dtype; the library zero-fills it and grad_value.
  * Workspace: msda_backward_workspace_bytes(prob, flags) (fp32 accumulation image for 16-bit storage).
+ * MSDA_BWD_VALUE_COLSUM (with NEED_IMG, fp16/bf16 storage, msda_module_colsum_supported(prob) == 1): the rounding pass
+ * that turns the fp32 accumulation image into grad_value also sums it over (b, pixel); on completion the H*D fp32 column
+ * sums sit at (char *)workspace + msda_module_colsum_offset(prob).  They are what autograd would compute as
+ * grad_value.sum over rows for the bias of the value projection (frontend.py:259) with a separate reduction kernel.
+ * msda_backward_workspace_bytes(prob, flags) includes the extra H*D floats when the flag is passed.
  */
 int msda_module_supported(const msda_problem *prob, int ref_dim);
+int msda_module_colsum_supported(const msda_problem *prob);
+size_t msda_module_colsum_offset(const msda_problem *prob);
 int msda_module_forward(void *out, const void *value, const int64_t *img_shapes, const void *proj, const void *ref,
                         int ref_dim, const msda_problem *prob, void *stream);
 int msda_module_backward(void *grad_value, void *grad_proj, float *grad_ref, const void *grad_out, const void *value,

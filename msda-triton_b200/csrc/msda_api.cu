@@ -181,9 +181,24 @@ size_t msda_backward_workspace_bytes(const msda_problem *prob, int flags) {
             return msda::detq_workspace_bytes(a);
         return msda::det_supported(a) ? msda::det_workspace_bytes(a) : 0;
     }
-    if (prob->dtype == MSDA_DTYPE_F16 || prob->dtype == MSDA_DTYPE_BF16)
+    if (prob->dtype == MSDA_DTYPE_F16 || prob->dtype == MSDA_DTYPE_BF16) {
+        if ((flags & MSDA_BWD_VALUE_COLSUM) && msda_module_colsum_supported(prob))
+            return msda_module_colsum_offset(prob) + sizeof(float) * (size_t)prob->H * prob->D;
         return sizeof(float) * (size_t)prob->B * prob->Npix * prob->H * prob->D;
+    }
     return 0;
+}
+
+int msda_module_colsum_supported(const msda_problem *prob) {
+    if (validate(prob) != MSDA_OK) return 0;
+    const long long n = (long long)prob->B * prob->Npix * prob->H * prob->D;
+    return msda::round_colsum_supported(prob->dtype, (int)prob->D, (int)(prob->H * prob->D), n) ? 1 : 0;
+}
+
+size_t msda_module_colsum_offset(const msda_problem *prob) {
+    if (validate(prob) != MSDA_OK) return 0;
+    const size_t accum = sizeof(float) * (size_t)prob->B * prob->Npix * prob->H * prob->D;
+    return (accum + 255) / 256 * 256;
 }
 
 int msda_backward(void *grad_img, void *grad_points, void *grad_weights, const void *grad_out, const void *img,
@@ -386,6 +401,11 @@ int msda_module_backward(void *grad_value, void *grad_proj, float *grad_ref, con
     const bool need_img = flags & MSDA_BWD_NEED_IMG, need_proj = flags & (MSDA_BWD_NEED_POINTS | MSDA_BWD_NEED_WEIGHTS),
                need_ref = flags & MSDA_BWD_NEED_REF;
     if (!need_img && !need_proj && !need_ref) return MSDA_OK;
+    const bool staged = need_img && prob->dtype != MSDA_DTYPE_F32;
+    const bool want_colsum = (flags & MSDA_BWD_VALUE_COLSUM) != 0;
+    if (want_colsum && !(staged && msda_module_colsum_supported(prob)))
+        return fail(MSDA_ERR_BAD_MODE, "msda_module_backward: MSDA_BWD_VALUE_COLSUM needs MSDA_BWD_NEED_IMG, fp16/bf16 "
+                                       "storage and msda_module_colsum_supported(prob)");
     const size_t es = dtype_size(prob->dtype);
     const size_t img_elems = (size_t)prob->B * prob->Npix * prob->H * prob->D;
     const bool no_units = prob->B == 0 || prob->Q == 0;
@@ -396,21 +416,29 @@ int msda_module_backward(void *grad_value, void *grad_proj, float *grad_ref, con
     if ((need_img && !grad_value && img_elems > 0) || (!no_units && ((need_proj && !grad_proj) || (need_ref && !grad_ref))))
         return fail(MSDA_ERR_NULL_POINTER, "msda_module_backward: a requested gradient buffer is NULL");
 
-    const bool staged = need_img && prob->dtype != MSDA_DTYPE_F32;
     void *accum = grad_value;
     size_t accum_bytes = img_elems * es;
     if (staged) {
-        const size_t want = img_elems * sizeof(float);
+        const size_t want = want_colsum ? msda_module_colsum_offset(prob) + sizeof(float) * (size_t)prob->H * prob->D
+                                        : img_elems * sizeof(float);
         if ((!workspace && want > 0) || workspace_bytes < want || !aligned(workspace, 16))
             return fail(MSDA_ERR_WORKSPACE, "msda_module_backward: 16-byte aligned workspace of %zu bytes required, got %zu",
                         want, workspace_bytes);
         accum = workspace;
-        accum_bytes = want;
+        accum_bytes = img_elems * sizeof(float);
     }
+    float *colsum = want_colsum
+        ? reinterpret_cast<float *>(static_cast<unsigned char *>(workspace) + msda_module_colsum_offset(prob)) : nullptr;
     cudaError_t e;
     if (need_img && img_elems > 0) {
-        e = cudaMemsetAsync(accum, 0, accum_bytes, st);
+        // no queries: nothing will be accumulated or rounded, so the zeros go straight into grad_value
+        e = (staged && no_units) ? cudaMemsetAsync(grad_value, 0, img_elems * es, st)
+                                 : cudaMemsetAsync(accum, 0, accum_bytes, st);
         if (e != cudaSuccess) return fail_cuda(e, "msda_module_backward zero-fill");
+    }
+    if (colsum && (no_units || img_elems == 0)) {   // nothing is accumulated: the sums are zero
+        e = cudaMemsetAsync(colsum, 0, sizeof(float) * (size_t)prob->H * prob->D, st);
+        if (e != cudaSuccess) return fail_cuda(e, "msda_module_backward zero-fill of the column sums");
     }
     if (need_ref && !no_units) {
         e = cudaMemsetAsync(grad_ref, 0, sizeof(float) * (size_t)prob->B * prob->Q * ref_dim, st);
@@ -440,7 +468,7 @@ int msda_module_backward(void *grad_value, void *grad_proj, float *grad_ref, con
     if (e != cudaSuccess) return fail_cuda(e, "msda_module_backward launch");
     if (staged) {
         e = msda::launch_round_grad_img(grad_value, static_cast<const float *>(accum), (long long)img_elems, prob->dtype,
-                                        (int)prob->D, (int)(prob->D / 8), st);
+                                        (int)prob->D, (int)(prob->D / 8), st, colsum, (int)(prob->H * prob->D));
         if (e != cudaSuccess) return fail_cuda(e, "msda_module_backward grad_value rounding");
     }
     return MSDA_OK;

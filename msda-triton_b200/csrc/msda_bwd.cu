@@ -266,11 +266,89 @@ __global__ void __launch_bounds__(256) round_grad_img_vec8_kernel(T *__restrict_
     }
 }
 
+// The same with the tuned kernels' permuted rows (D = 8 * lanes channels per head row; channel 8j + 4h + e sits at position
+// 4*lanes*h + 4j + e): output channels 8j .. 8j+7 are the two 16-byte pieces at positions 4j and 4*lanes + 4j.  Optionally
+// the pass also leaves the COLUMN SUMS of what it reads -- sum over (b, pixel) of grad_value[b, pixel, h, c], fp32, one per
+// (h, c) -- in `colsum`: that is the bias gradient of the projection that produced `value` (frontend.py:259,
+// img_input_proj), which torch otherwise computes with a reduction kernel over the rounded tensor (B=8 x 22 223 pixels x
+// 256 columns: ~100 us for 91 MB; here it rides on data that is in registers anyway).
+// Requires blockDim.x % (HD / 8) == 0 (so that a thread keeps its columns over the grid stride) and HD <= 2048.
+template <typename T, bool COLSUM>
+__global__ void __launch_bounds__(256) round_grad_img_perm_vec8_kernel(T *__restrict__ dst, const float *__restrict__ src,
+                                                                       long long n8, int lanes, float *__restrict__ colsum,
+                                                                       int HD) {
+    __shared__ float s_sum[COLSUM ? 2048 : 1];
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if constexpr (COLSUM) {
+        for (int c = threadIdx.x; c < HD; c += blockDim.x) s_sum[c] = 0.0f;
+        __syncthreads();
+    }
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+        const long long row = i / lanes;          // head row = D channels = `lanes` chunks of 8
+        const int j = (int)(i - row * lanes);
+        const float *base = src + row * (8LL * lanes);
+        const float4 a = __ldcs(reinterpret_cast<const float4 *>(base + 4 * j));
+        const float4 b = __ldcs(reinterpret_cast<const float4 *>(base + 4 * lanes + 4 * j));
+        Pack<T, 8> o;
+        o.v[0] = Traits<T>::from_ct(a.x);
+        o.v[1] = Traits<T>::from_ct(a.y);
+        o.v[2] = Traits<T>::from_ct(a.z);
+        o.v[3] = Traits<T>::from_ct(a.w);
+        o.v[4] = Traits<T>::from_ct(b.x);
+        o.v[5] = Traits<T>::from_ct(b.y);
+        o.v[6] = Traits<T>::from_ct(b.z);
+        o.v[7] = Traits<T>::from_ct(b.w);
+        reinterpret_cast<Pack<T, 8> *>(dst)[i] = o;
+        if constexpr (COLSUM) {
+            acc[0] += a.x, acc[1] += a.y, acc[2] += a.z, acc[3] += a.w;
+            acc[4] += b.x, acc[5] += b.y, acc[6] += b.z, acc[7] += b.w;
+        }
+    }
+    if constexpr (COLSUM) {
+        // the thread's chunk column never changes: stride is a multiple of blockDim.x, which is a multiple of HD / 8
+        const int col = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) % (HD / 8)) * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(&s_sum[col + e], acc[e]);
+        __syncthreads();
+        for (int c = threadIdx.x; c < HD; c += blockDim.x) red_add_v1(colsum + c, s_sum[c]);
+    }
+}
+
+bool round_colsum_supported(int dtype, int D, int HD, long long n) {
+    return (dtype == 1 || dtype == 2) && D % 8 == 0 && HD % 8 == 0 && HD <= 2048 && 256 % (HD / 8) == 0 && n % 8 == 0;
+}
+
 cudaError_t launch_round_grad_img(void *dst, const float *src, long long n, int dtype, int D, int permuted_lanes,
-                                  cudaStream_t st) {
+                                  cudaStream_t st, float *colsum, int HD) {
     if (n <= 0) return cudaSuccess;
-    if (permuted_lanes == 0 && n % 8 == 0 && reinterpret_cast<uintptr_t>(dst) % 16 == 0 &&
-        reinterpret_cast<uintptr_t>(src) % 16 == 0 && (dtype == 1 || dtype == 2)) {
+    const bool vec_ok = n % 8 == 0 && reinterpret_cast<uintptr_t>(dst) % 16 == 0 &&
+                        reinterpret_cast<uintptr_t>(src) % 16 == 0 && (dtype == 1 || dtype == 2);
+    if (colsum && !(vec_ok && permuted_lanes > 0 && permuted_lanes * 8 == D && round_colsum_supported(dtype, D, HD, n)))
+        return cudaErrorNotSupported;
+    if (vec_ok && permuted_lanes > 0 && permuted_lanes * 8 == D) {
+        const long long n8 = n / 8;
+        long long want8 = (n8 + 255) / 256;
+        const int grid8 = (int)(want8 > 148 * 16 ? 148 * 16 : want8);
+        if (colsum) {
+            const cudaError_t e = cudaMemsetAsync(colsum, 0, sizeof(float) * (size_t)HD, st);
+            if (e != cudaSuccess) return e;
+            if (dtype == 1)
+                round_grad_img_perm_vec8_kernel<__half, true>
+                    <<<grid8, 256, 0, st>>>(static_cast<__half *>(dst), src, n8, permuted_lanes, colsum, HD);
+            else
+                round_grad_img_perm_vec8_kernel<__nv_bfloat16, true>
+                    <<<grid8, 256, 0, st>>>(static_cast<__nv_bfloat16 *>(dst), src, n8, permuted_lanes, colsum, HD);
+        } else if (dtype == 1) {
+            round_grad_img_perm_vec8_kernel<__half, false>
+                <<<grid8, 256, 0, st>>>(static_cast<__half *>(dst), src, n8, permuted_lanes, nullptr, 0);
+        } else {
+            round_grad_img_perm_vec8_kernel<__nv_bfloat16, false>
+                <<<grid8, 256, 0, st>>>(static_cast<__nv_bfloat16 *>(dst), src, n8, permuted_lanes, nullptr, 0);
+        }
+        return cudaGetLastError();
+    }
+    if (permuted_lanes == 0 && vec_ok) {
         const long long n8 = n / 8;
         long long want8 = (n8 + 255) / 256;
         const int grid8 = (int)(want8 > 148 * 16 ? 148 * 16 : want8);

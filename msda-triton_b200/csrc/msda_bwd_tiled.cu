@@ -282,7 +282,7 @@ __device__ __forceinline__ void dense_owner_wave(const KernelArgs &a, const Leve
 // through the same saturated LSU plus the partner's weight arithmetic, which is no cheaper.
 // OPT-IN: MSDA_B200_BWD_AGG=1 (tests keep it correct).
 template <typename T, int LANES, int LK, bool BORDER, int NB, int THREADS, bool FUSED, int VEC, bool PADDED,
-          bool SPLIT, bool QUANT = false, bool AGG = false, int NOWN = 0, int DPF = 2, bool PIPE = false>
+          bool SPLIT, bool QUANT = false, bool AGG = false, int NOWN = 0, int DPF = 2, bool PIPE = false, int NA = 0>
 __global__ void __launch_bounds__(THREADS, 1)
     msda_bwd_tiled_kernel(const KernelArgs a, const WaveSchedule ws, const int subs_arg) {
     constexpr bool DENSE = NOWN > 0;   // the last NOWN warps of the CTA are owner warps (see the DENSE notes above)
@@ -489,7 +489,13 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll
                 for (int n = 0; n < NB; ++n) {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) raw[n][c] = gather_slice<VEC * (int)sizeof(T)>(lane_base, cur.o[n][c]);
+                    for (int c = 0; c < 4; ++c) {
+                        // NA: the first NA point slots (the finest levels) are gathered without allocating in L1
+                        if ((jj0 + n) * PPL + pp < NA)
+                            raw[n][c] = gather_slice_na<VEC * (int)sizeof(T)>(lane_base, cur.o[n][c]);
+                        else
+                            raw[n][c] = gather_slice<VEC * (int)sizeof(T)>(lane_base, cur.o[n][c]);
+                    }
                 }
                 Exchanged nxt = cur;
                 if constexpr (PIPE) {
@@ -687,7 +693,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 
 template <typename T, int LANES, int LK, bool FUSED = false, int VEC = 16 / (int)sizeof(T), bool PADDED = false,
           bool SPLIT = false, bool QUANT = false, bool AGG = false, int NOWN = 0, int DPF = 2, int THREADS = 512,
-          int NB = 2, bool PIPE = false>
+          int NB = 2, bool PIPE = false, int NA = 0>
 static cudaError_t launch_tiled_t(const KernelArgs &a, int sm_count, cudaStream_t st, int subs = 1) {
     constexpr int G = TiledCfg<T, LANES, LK>::G;
     if (!tiled_offsets_fit(a, sizeof(T), subs)) return cudaErrorNotSupported;
@@ -707,11 +713,19 @@ static cudaError_t launch_tiled_t(const KernelArgs &a, int sm_count, cudaStream_
         const cudaError_t e = acquire_pace_counter(st, &ws.pace);
         if (e != cudaSuccess) return e;
     }
+    if (tuning().carveout >= 0) {   // experiment knob: shared-memory carve-out (percent) = what is left for L1
+        cudaFuncSetAttribute(
+            msda_bwd_tiled_kernel<T, LANES, LK, true, NB, THREADS, FUSED, VEC, PADDED, SPLIT, QUANT, AGG, NOWN, DPF, PIPE, NA>,
+            cudaFuncAttributePreferredSharedMemoryCarveout, tuning().carveout);
+        cudaFuncSetAttribute(
+            msda_bwd_tiled_kernel<T, LANES, LK, false, NB, THREADS, FUSED, VEC, PADDED, SPLIT, QUANT, AGG, NOWN, DPF, PIPE, NA>,
+            cudaFuncAttributePreferredSharedMemoryCarveout, tuning().carveout);
+    }
     if (a.border)
-        msda_bwd_tiled_kernel<T, LANES, LK, true, NB, THREADS, FUSED, VEC, PADDED, SPLIT, QUANT, AGG, NOWN, DPF, PIPE>
+        msda_bwd_tiled_kernel<T, LANES, LK, true, NB, THREADS, FUSED, VEC, PADDED, SPLIT, QUANT, AGG, NOWN, DPF, PIPE, NA>
             <<<grid, THREADS, 0, st>>>(a, ws, subs);
     else
-        msda_bwd_tiled_kernel<T, LANES, LK, false, NB, THREADS, FUSED, VEC, PADDED, SPLIT, QUANT, AGG, NOWN, DPF, PIPE>
+        msda_bwd_tiled_kernel<T, LANES, LK, false, NB, THREADS, FUSED, VEC, PADDED, SPLIT, QUANT, AGG, NOWN, DPF, PIPE, NA>
             <<<grid, THREADS, 0, st>>>(a, ws, subs);
     return cudaGetLastError();
 }
@@ -876,6 +890,10 @@ cudaError_t launch_backward_tiled(const KernelArgs &a, int dtype, int sm_count, 
             if (shape < 0) {
                 const long long tiles = (long long)a.B * a.H * ((a.Q + 3) / 4);
                 shape = tiles >= 16LL * 16 * sm_count ? 1 : 0;
+                // + the finest level (first K point slots) gathered without allocating in L1, as in the forward: its
+                // 512 KB per (b,h) slice cannot stay there and only evicts the coarse levels (another 1-2 %)
+                // (measured: -1 % time, but the no-allocate loads also lose their lines in L2 -- DRAM reads 165 -> 239 MB per
+                // launch, 1.34x the algorithmic bytes -- so it stays a knob, MSDA_B200_BWD_SHAPE=6)
             }
             if (shape == 1)
                 return launch_tiled_t<float, 8, 16, false, 4, false, false, false, false, 0, 2, 384, 2>(a, sm_count, st);
@@ -887,6 +905,12 @@ cudaError_t launch_backward_tiled(const KernelArgs &a, int dtype, int sm_count, 
                 return launch_tiled_t<float, 8, 16, false, 4, false, false, false, false, 0, 2, 512, 2, true>(a, sm_count, st);
             if (shape == 5)
                 return launch_tiled_t<float, 8, 16, false, 4, false, false, false, false, 0, 2, 384, 4, true>(a, sm_count, st);
+            if (shape == 6)   // 12 x 168, first 4 / 8 / 12 point slots gathered with no-allocate loads
+                return launch_tiled_t<float, 8, 16, false, 4, false, false, false, false, 0, 2, 384, 2, false, 4>(a, sm_count, st);
+            if (shape == 7)
+                return launch_tiled_t<float, 8, 16, false, 4, false, false, false, false, 0, 2, 384, 2, false, 8>(a, sm_count, st);
+            if (shape == 8)
+                return launch_tiled_t<float, 8, 16, false, 4, false, false, false, false, 0, 2, 384, 2, false, 12>(a, sm_count, st);
             return launch_tiled_t<float, 8, 16>(a, sm_count, st);
         }
         if (a.D == 64) return launch_tiled_t<float, 16, 16>(a, sm_count, st);

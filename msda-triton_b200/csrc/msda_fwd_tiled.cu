@@ -170,6 +170,12 @@ static cudaError_t launch_tiled_cfg(const KernelArgs &a, int sm_count, cudaStrea
         const cudaError_t e = acquire_pace_counter(st, &ws.pace);
         if (e != cudaSuccess) return e;
     }
+    if (tuning().carveout >= 0) {   // experiment knob: shared-memory carve-out (percent) = what is left for L1
+        cudaFuncSetAttribute(msda_fwd_tiled_kernel<T, LANES, LK, true, NB, THREADS, FUSED, PADDED, VECB, NAK>,
+                             cudaFuncAttributePreferredSharedMemoryCarveout, tuning().carveout);
+        cudaFuncSetAttribute(msda_fwd_tiled_kernel<T, LANES, LK, false, NB, THREADS, FUSED, PADDED, VECB, NAK>,
+                             cudaFuncAttributePreferredSharedMemoryCarveout, tuning().carveout);
+    }
     if (a.border)
         msda_fwd_tiled_kernel<T, LANES, LK, true, NB, THREADS, FUSED, PADDED, VECB, NAK><<<grid, THREADS, 0, st>>>(a, ws);
     else

@@ -41,8 +41,11 @@ cudaError_t launch_backward_det(const KernelArgs &a, int dtype, int vec, void *w
 
 // grad_img epilogue for 16-bit storage: rounds the fp32 accumulation image to T.
 // permuted_lanes = D/8 when the image was written by the tuned kernels (channel-permuted rows), 0 for natural order.
+// colsum != nullptr: additionally the fp32 column sums over (b, pixel) of the HD = H*D columns (zeroed here first); only
+// for permuted rows with round_colsum_supported(); cudaErrorNotSupported otherwise.
 cudaError_t launch_round_grad_img(void *dst, const float *src, long long n, int dtype, int D, int permuted_lanes,
-                                  cudaStream_t st);
+                                  cudaStream_t st, float *colsum = nullptr, int HD = 0);
+bool round_colsum_supported(int dtype, int D, int HD, long long n);
 
 // Arrival counter for wave pacing (msda_pace.cu): *slot = a device word zeroed on `st`, or nullptr when pacing is off.
 cudaError_t acquire_pace_counter(cudaStream_t st, unsigned **slot);

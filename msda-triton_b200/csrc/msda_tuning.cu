@@ -35,6 +35,7 @@ void read_env() {
     t.bwd_dense = env_int("MSDA_B200_BWD_DENSE", -1);
     t.dense_prefetch = env_int("MSDA_B200_DENSE_PF", 3);
     t.bwd_shape = env_int("MSDA_B200_BWD_SHAPE", -1);
+    t.carveout = env_int("MSDA_B200_CARVEOUT", -1);
     t.det_variant = env_int("MSDA_B200_DET_VARIANT", -1);
     g_tuning = t;
 }

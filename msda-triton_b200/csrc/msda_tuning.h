@@ -23,6 +23,7 @@ struct Tuning {
     int dense_prefetch = 3;    // MSDA_B200_DENSE_PF=3|4       : units an owner warp keeps in flight
     int bwd_shape = -1;        // MSDA_B200_BWD_SHAPE=0..5     : fp32 backward launch shape: 16 warps x 128 regs | 12 x 168 | experiments
                                //                                (default: 12 x 168 for problems with many warp tiles per warp)
+    int carveout = -1;         // MSDA_B200_CARVEOUT=0..100    : preferred shared-memory carve-out of the tuned kernels (experiment)
     int det_variant = -1;      // MSDA_B200_DET_VARIANT=0|1    : deterministic grad_img: 0 = radix sort, 1 = slice binning
 };
 

@@ -17,6 +17,7 @@ ABI_VERSION = 1
 DTYPE_F32, DTYPE_F16, DTYPE_BF16, DTYPE_F64 = 0, 1, 2, 3
 PAD_ZEROS, PAD_BORDER = 0, 1
 BWD_NEED_IMG, BWD_NEED_POINTS, BWD_NEED_WEIGHTS, BWD_DETERMINISTIC, BWD_NEED_REF = 1, 2, 4, 8, 16
+BWD_VALUE_COLSUM = 32
 
 
 class MsdaPeerCtx(ctypes.Structure):
@@ -59,6 +60,10 @@ def _load() -> ctypes.CDLL:
     lib.msda_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, pp, ci, vp, sz, vp]
     lib.msda_module_supported.restype = ci
     lib.msda_module_supported.argtypes = [pp, ci]
+    lib.msda_module_colsum_supported.restype = ci
+    lib.msda_module_colsum_supported.argtypes = [pp]
+    lib.msda_module_colsum_offset.restype = ctypes.c_size_t
+    lib.msda_module_colsum_offset.argtypes = [pp]
     lib.msda_module_forward.restype = ci
     lib.msda_module_forward.argtypes = [vp, vp, vp, vp, vp, ci, pp, vp]
     lib.msda_module_backward.restype = ci

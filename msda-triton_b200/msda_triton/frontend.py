@@ -32,6 +32,10 @@ PaddingMode = Literal["border", "zeros"]
 def _fused_module_enabled() -> bool:
     return os.environ.get("MSDA_B200_FUSED_MODULE", "1") != "0"
 
+
+def _fused_value_proj_enabled() -> bool:
+    return os.environ.get("MSDA_B200_FUSED_VALUE_PROJ", "1") != "0"
+
 # dtypes of the CUDA route: the reference's three (frontend.py:84) plus bf16, which its Triton helper rejects
 # (kernels.py:40-41) and therefore sends down the torch route.
 CUDA_DTYPES = (torch.float16, torch.bfloat16, torch.float32, torch.float64)
@@ -123,6 +127,55 @@ class _B200ModuleCoreFunction(torch.autograd.Function):
         gvalue, gproj, gref = kernels.b200_module_core_bwd(
             out_grad, value, img_shapes, projection, reference_points, ctx.padding_mode, ctx.align_corners, needs=needs)
         return gvalue, None, gproj, gref, None, None
+
+
+class _B200ValueProjCoreFunction(torch.autograd.Function):
+    """``img_input_proj`` (frontend.py:259 of the reference: ``value = Linear(img)``) AND the module core as one autograd
+    node, for 16-bit parameters.  Forward: the same cuBLAS GEMM torch would run, then the fused core kernel.  Backward:
+    the core kernel's rounding pass (fp32 accumulation image -> 16-bit grad_value) also returns the column sums of what
+    it rounds, which ARE the bias gradient of the projection -- torch computes them with a separate reduction kernel
+    over the 16-bit tensor (~100 us for the B=8 x 22 223-pixel decoder pyramid) -- and the two remaining gradients are
+    the two GEMMs autograd would issue.  Used outside autocast only (under autocast the core runs in fp32 and has no
+    rounding pass)."""
+
+    @staticmethod
+    def forward(ctx, img, weight, bias, img_shapes, projection, reference_points, heads, padding_mode, align_corners):
+        batch, num_pixels, _ = img.shape
+        hidden = weight.shape[0]
+        value = torch.nn.functional.linear(img, weight, bias).view(batch, num_pixels, heads, hidden // heads)
+        ctx.save_for_backward(img, weight, value, img_shapes, projection, reference_points)
+        ctx.padding_mode = padding_mode
+        ctx.align_corners = align_corners
+        return kernels.b200_module_core_fwd(value, img_shapes, projection, reference_points, padding_mode, align_corners)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, out_grad):
+        img, weight, value, img_shapes, projection, reference_points = ctx.saved_tensors
+        need_img, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        need_value = need_img or need_w or need_b
+        res = kernels.b200_module_core_bwd(
+            out_grad, value, img_shapes, projection, reference_points, ctx.padding_mode, ctx.align_corners,
+            needs=(need_value, ctx.needs_input_grad[4], ctx.needs_input_grad[5]), value_colsum=need_b)
+        gvalue, gproj, gref = res[:3]
+        gimg = gweight = gbias = None
+        if need_value:
+            g2 = gvalue.view(-1, weight.shape[0])
+            if need_img:
+                gimg = torch.matmul(g2, weight).view(img.shape)
+            if need_w:
+                gweight = torch.matmul(g2.t(), img.reshape(-1, img.shape[-1]))
+            if need_b:
+                gbias = res[3].reshape(-1).to(weight.dtype)
+        return gimg, gweight, gbias, None, gproj, gref, None, None, None
+
+
+def fused_value_proj_core(img, weight, bias, img_shapes, projection, reference_points, heads: int,
+                          padding_mode: PaddingMode, align_corners: bool) -> torch.Tensor:
+    """``core(Linear(img; weight, bias).view(B, I, heads, C), ...)`` with the bias gradient taken from the core's own
+    rounding pass; returns ``[B, N, H, C]``.  16-bit dtypes, see kernels.module_value_colsum_supported."""
+    return _B200ValueProjCoreFunction.apply(img, weight, bias, img_shapes, projection, reference_points, int(heads),
+                                            padding_mode, bool(align_corners))
 
 
 def fused_module_core(value, img_shapes, projection, reference_points, padding_mode: PaddingMode,
@@ -272,10 +325,30 @@ class MultiscaleDeformableAttention(nn.Module):
 
         # offsets and logits come out of ONE projection, interleaved as (..., point, 3) (frontend.py:253-257)
         projected = self.query_input_proj(queries).reshape(batch, num_queries, heads, levels, points, 3)
-        value = self.img_input_proj(img).reshape(batch, num_pixels, heads, self.hidden_dim // heads)
         if reference_points.shape[-1] not in (2, 4):
             raise ValueError(
                 f"`reference_points` should have the last dim either 2 or 4, but got {reference_points.shape[-1]}.")
+
+        # 16-bit parameters on CUDA, training: the value projection and the core as ONE autograd node, so that the bias
+        # gradient of img_input_proj comes out of the core's rounding pass instead of a reduction kernel of its own
+        proj_w, proj_b = self.img_input_proj.weight, self.img_input_proj.bias
+        if (img.is_cuda and projected.is_cuda and reference_points.is_cuda
+                and img.dtype in (torch.float16, torch.bfloat16) and proj_b is not None
+                and proj_w.dtype == img.dtype == projected.dtype == reference_points.dtype
+                and (proj_b.requires_grad and torch.is_grad_enabled())
+                and not torch.is_autocast_enabled("cuda") and not torch.compiler.is_compiling()
+                and _fused_module_enabled() and _fused_value_proj_enabled() and not kernels.is_deterministic()
+                and img.dim() == 3 and img.is_contiguous()):
+            shape4 = (batch, num_pixels, heads, self.hidden_dim // heads)
+            if (kernels.module_value_colsum_shape_supported(img.dtype, heads, shape4[3])
+                    and kernels.module_core_shape_supported(img.dtype, shape4, projected, reference_points)):
+                if img_shapes.device != img.device:
+                    img_shapes = img_shapes.to(img.device, non_blocking=True)
+                out = fused_value_proj_core(img, proj_w, proj_b, img_shapes, projected, reference_points, heads,
+                                            self.padding_mode, self.align_corners)
+                return self.query_output_proj(out.reshape(batch, num_queries, self.hidden_dim))
+
+        value = self.img_input_proj(img).reshape(batch, num_pixels, heads, self.hidden_dim // heads)
 
         # CUDA fast path: softmax, sampling-point arithmetic and the operator in one kernel (no materialised
         # sampling_points / attention_weights).  Set MSDA_B200_FUSED_MODULE=0 to take the composed path below.

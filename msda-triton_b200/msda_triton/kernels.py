@@ -233,17 +233,25 @@ def module_core_supported_static(value: torch.Tensor, proj: torch.Tensor, ref: t
     """The eligibility rule of :func:`module_core_supported` (``msda_module_supported`` in the library) restated on
     shapes and dtypes only, for traced programs (torch.compile cannot call into ctypes); a CPU test keeps the two in
     step."""
-    if value.device.type != "cuda" or value.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+    if value.device.type != "cuda" or value.dim() != 4:
         return False
-    if not (value.dtype == proj.dtype == ref.dtype) or value.dim() != 4 or proj.dim() != 6 or ref.dim() != 3:
+    return module_core_shape_supported(value.dtype, tuple(value.shape), proj, ref)
+
+
+def module_core_shape_supported(dtype, value_shape, proj: torch.Tensor, ref: torch.Tensor) -> bool:
+    """:func:`module_core_supported_static` for a value tensor that does not exist yet (dtype + ``[B, I, H, C]`` shape)."""
+    if dtype not in (torch.float32, torch.float16, torch.bfloat16):
         return False
-    batch, num_pixels, heads, channels = value.shape
+    if not (dtype == proj.dtype == ref.dtype) or proj.dim() != 6 or ref.dim() != 3:
+        return False
+    batch, num_pixels, heads, channels = value_shape
+    elem_size = torch.empty((), dtype=dtype).element_size()
     queries, levels, points = proj.shape[1], proj.shape[3], proj.shape[4]
     if not (channels in (32, 64) and levels * points == 16 and levels <= 8 and proj.shape[5] == 3
             and ref.shape[2] in (2, 4)):
         return False
     # 32-bit offset arithmetic of the tuned kernels (tiled_offsets_fit in csrc/msda_tiled.cuh)
-    return num_pixels * heads * channels * value.element_size() < 2 ** 28 and batch * heads * queries < 2 ** 31
+    return num_pixels * heads * channels * elem_size < 2 ** 28 and batch * heads * queries < 2 ** 31
 
 
 def b200_module_core_fwd(value, img_shapes, proj, ref, padding_mode, align_corners) -> torch.Tensor:
@@ -261,9 +269,22 @@ def b200_module_core_fwd(value, img_shapes, proj, ref, padding_mode, align_corne
     return out
 
 
+def module_value_colsum_supported(value: torch.Tensor) -> bool:
+    """Whether the fused module backward can also return the column sums of grad_value (the bias gradient of the value
+    projection): 16-bit storage and a hidden width the rounding pass can keep per thread (H*D / 8 divides 256)."""
+    return value.dim() == 4 and module_value_colsum_shape_supported(value.dtype, int(value.shape[2]), int(value.shape[3]))
+
+
+def module_value_colsum_shape_supported(dtype, heads: int, channels: int) -> bool:
+    hd = heads * channels
+    return (dtype in (torch.float16, torch.bfloat16) and channels % 8 == 0 and 0 < hd <= 2048 and 256 % (hd // 8) == 0)
+
+
 def b200_module_core_bwd(out_grad, value, img_shapes, proj, ref, padding_mode, align_corners,
-                         needs: Sequence[bool] = (True, True, True)):
-    """Returns (grad_value, grad_proj, grad_ref); grad_ref comes back in the storage dtype."""
+                         needs: Sequence[bool] = (True, True, True), value_colsum: bool = False):
+    """Returns (grad_value, grad_proj, grad_ref); grad_ref comes back in the storage dtype.  ``value_colsum=True``
+    (16-bit storage, see module_value_colsum_supported): a fourth result, the fp32 ``[H, D]`` sums of grad_value over
+    (batch, pixel) -- the bias gradient of the projection that produced ``value`` -- computed by the rounding pass."""
     value, proj, ref = _dense(value), _dense(proj), _dense(ref)
     shapes = _shapes_i64(img_shapes)
     prob = _module_problem(value, shapes, proj, ref, padding_mode, align_corners)
@@ -271,12 +292,15 @@ def b200_module_core_bwd(out_grad, value, img_shapes, proj, ref, padding_mode, a
     need_value, need_proj, need_ref = (bool(n) for n in needs)
     flags = (_lib.BWD_NEED_IMG * need_value) | ((_lib.BWD_NEED_POINTS | _lib.BWD_NEED_WEIGHTS) * need_proj) \
         | (_lib.BWD_NEED_REF * need_ref)
+    value_colsum = bool(value_colsum) and need_value
+    if value_colsum:
+        flags |= _lib.BWD_VALUE_COLSUM
     gvalue = torch.empty(value.shape, dtype=value.dtype, device=value.device) if need_value else None
     gproj = torch.empty(proj.shape, dtype=proj.dtype, device=value.device) if need_proj else None
     gref32 = torch.empty(ref.shape, dtype=torch.float32, device=value.device) if need_ref else None
     lib = _lib.get_lib()
     with _on_device_of(value) as stream:
-        ws_bytes = int(lib.msda_backward_workspace_bytes(ctypes.byref(prob), flags & 7))
+        ws_bytes = int(lib.msda_backward_workspace_bytes(ctypes.byref(prob), flags & (7 | _lib.BWD_VALUE_COLSUM)))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=value.device) if ws_bytes else None
         rc = lib.msda_module_backward(
             _ptr(gvalue), _ptr(gproj), _ptr(gref32), _ptr(gout), _ptr(value), _ptr(shapes), _ptr(proj), _ptr(ref),
@@ -284,6 +308,11 @@ def b200_module_core_bwd(out_grad, value, img_shapes, proj, ref, padding_mode, a
     if rc:
         _lib.check(rc, "msda_module_backward")
     gref = (gref32 if ref.dtype == torch.float32 else gref32.to(ref.dtype)) if need_ref else None
+    if value_colsum:
+        off = int(lib.msda_module_colsum_offset(ctypes.byref(prob)))
+        hd = value.shape[2] * value.shape[3]
+        colsum = ws[off:off + 4 * hd].view(torch.float32).reshape(value.shape[2], value.shape[3])
+        return gvalue, gproj, gref, colsum
     return gvalue, gproj, gref
 
 

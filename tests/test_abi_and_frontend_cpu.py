@@ -35,7 +35,8 @@ def test_header_declares_the_expected_entry_points():
     assert declared_symbols() == sorted([
         "msda_abi_version", "msda_last_error", "msda_forward", "msda_backward_workspace_bytes", "msda_backward",
         "msda_level_table", "msda_probe_gather", "msda_probe_scatter", "msda_module_supported", "msda_module_forward",
-        "msda_module_backward", "msda_reload_tuning", "msda_peer_all_gather", "msda_peer_reduce_scatter"])
+        "msda_module_backward", "msda_reload_tuning", "msda_peer_all_gather", "msda_peer_reduce_scatter",
+        "msda_module_colsum_supported", "msda_module_colsum_offset"])
 
 
 def test_peer_entry_points_validate_without_a_gpu(libpath):
@@ -278,3 +279,27 @@ def test_product_package_never_touches_the_oracle():
         if "import oracle" in text or "from oracle" in text or "msda_oracle" in text or "oracle/" in text:
             offenders.append(str(path))
     assert not offenders, offenders
+
+
+def test_value_colsum_workspace_contract(libpath):
+    """MSDA_BWD_VALUE_COLSUM: 16-bit storage only; the H*D column sums live behind the (256-byte padded) accumulation image."""
+    from msda_triton import _lib
+    lib = _lib.get_lib()
+    for dtype, ok in ((2, 1), (1, 1), (0, 0)):
+        prob = _lib.MsdaProblem(2, 85, 8, 32, 10, 4, 4, dtype, 0, 0, 0)
+        assert lib.msda_module_colsum_supported(ctypes.byref(prob)) == ok
+        accum = 4 * 2 * 85 * 8 * 32
+        assert lib.msda_module_colsum_offset(ctypes.byref(prob)) == (accum + 255) // 256 * 256
+        plain = lib.msda_backward_workspace_bytes(ctypes.byref(prob), 1)
+        with_sums = lib.msda_backward_workspace_bytes(ctypes.byref(prob), 1 | _lib.BWD_VALUE_COLSUM)
+        if ok:
+            assert plain == accum and with_sums == (accum + 255) // 256 * 256 + 4 * 8 * 32
+        else:
+            assert plain == 0 and with_sums == 0
+    wide = _lib.MsdaProblem(1, 85, 40, 64, 10, 4, 4, 2, 0, 0, 0)     # H*D = 2560 > 2048 columns
+    assert lib.msda_module_colsum_supported(ctypes.byref(wide)) == 0
+    # the flag on an fp32 problem is refused before anything touches the device
+    prob = _lib.MsdaProblem(2, 85, 8, 32, 10, 4, 4, 0, 0, 0, 0)
+    rc = lib.msda_module_backward(None, None, None, None, None, None, None, None, 2, ctypes.byref(prob),
+                                  1 | _lib.BWD_VALUE_COLSUM, None, 0, None)
+    assert rc == -4 and b"MSDA_BWD_VALUE_COLSUM" in lib.msda_last_error()      # MSDA_ERR_BAD_MODE

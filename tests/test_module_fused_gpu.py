@@ -308,3 +308,106 @@ def test_module_core_custom_op_opcheck():
     import msda_triton.ops  # noqa: F401  (registers the ops)
     torch.library.opcheck(torch.ops.msda_b200.module_forward.default, (value, shapes, proj, ref, "border", True),
                           test_utils=("test_schema", "test_faketensor", "test_autograd_registration"))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# value projection + core as one autograd node (16-bit parameters): img_input_proj's bias gradient comes out of the
+# core's rounding pass (MSDA_BWD_VALUE_COLSUM) instead of a reduction kernel of its own
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+@pytest.mark.parametrize("D", [32, 64])
+@pytest.mark.parametrize("needs_value", [True, False])
+def test_rounding_pass_column_sums(dtype, D, needs_value):
+    """The fourth result of the fused backward: fp32 sums over (batch, pixel) of the UNROUNDED grad_value."""
+    from msda_triton import kernels
+    g = torch.Generator().manual_seed(41)
+    B, Q, H, L, K = 3, 211, 8, 4, 4
+    pyramid = [(25, 42), (13, 21), (7, 11), (4, 6)]
+    npix = sum(h * w for h, w in pyramid)
+    value = torch.randn(B, npix, H, D, generator=g).to("cuda", dtype)
+    proj = torch.randn(B, Q, H, L, K, 3, generator=g).to("cuda", dtype)
+    ref = torch.rand(B, Q, 2, generator=g).to("cuda", dtype)
+    go = torch.randn(B, Q, H, D, generator=g).to("cuda", dtype)
+    shapes = torch.tensor(pyramid, device="cuda")
+    assert kernels.module_value_colsum_supported(value)
+    plain = kernels.b200_module_core_bwd(go, value, shapes, proj, ref, "zeros", False, needs=(True, True, True))
+    res = kernels.b200_module_core_bwd(go, value, shapes, proj, ref, "zeros", False,
+                                       needs=(needs_value, True, True), value_colsum=True)
+    if not needs_value:
+        assert len(res) == 3 and res[0] is None      # no grad_value, no sums
+        return
+    gvalue, gproj, gref, colsum = res
+    assert torch.equal(gproj, plain[1])                                   # no atomics there: same bits
+    for a, b in ((gvalue, plain[0]), (gref, plain[2])):                   # atomics: the order of the fp32 adds varies
+        assert_close(to_np(a), to_np(b), 2.0 ** -7, 2.0 ** -7 * float(b.float().abs().max()), "repeat run")
+    assert colsum.shape == (H, D) and colsum.dtype == torch.float32
+    # yardstick: fp64 sum of the fp32 gradient of the same operands (no 16-bit rounding of the addends on either side)
+    v32, p32, r32, g32 = (t.float() for t in (value, proj, ref, go))
+    want = kernels.b200_module_core_bwd(g32, v32, shapes, p32, r32, "zeros", False, needs=(True, False, False))[0]
+    want = want.double().sum((0, 1))
+    assert_close(to_np(colsum), to_np(want), 1e-4, 1e-4 * float(want.abs().max()), "column sums")
+    # and it is what summing the rounded tensor gives, up to that rounding
+    eps = 2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -11
+    rounded = gvalue.double().sum((0, 1))
+    bound = eps * gvalue.double().abs().sum((0, 1)) + 1e-6
+    assert bool(((colsum.double() - rounded).abs() <= bound).all())
+
+
+def test_rounding_pass_column_sums_without_queries():
+    from msda_triton import kernels
+    value = torch.randn(1, 85, 8, 32, device="cuda").bfloat16()
+    proj = torch.empty(1, 0, 8, 4, 4, 3, device="cuda", dtype=torch.bfloat16)
+    ref = torch.empty(1, 0, 2, device="cuda", dtype=torch.bfloat16)
+    go = torch.empty(1, 0, 8, 32, device="cuda", dtype=torch.bfloat16)
+    shapes = torch.tensor([(8, 8), (4, 4), (2, 2), (1, 1)], device="cuda")
+    gvalue, _, _, colsum = kernels.b200_module_core_bwd(go, value, shapes, proj, ref, "border", True, value_colsum=True)
+    assert float(gvalue.float().abs().max()) == 0.0 and float(colsum.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+@pytest.mark.parametrize("hidden", [256, 512], ids=["d32", "d64"])
+@pytest.mark.parametrize("coords", [2, 4])
+def test_module_value_projection_node_equals_separate_nodes(dtype, hidden, coords, monkeypatch):
+    """Same bf16 / fp16 module and inputs with and without the fused value-projection node: identical forward, the same
+    gradients (the two GEMMs are the ones autograd issues; the bias gradient is summed before instead of after the
+    rounding to 16 bits)."""
+    from msda_triton import MultiscaleDeformableAttention, frontend
+    torch.manual_seed(5)
+    emb, heads, levels, points = 256, 8, 4, 4
+    npix = sum(h * w for h, w in BENCH_PYRAMID)
+    img = torch.randn(2, npix, emb).to("cuda", dtype)
+    queries = torch.randn(2, 300, emb).to("cuda", dtype)
+    ref_pts = (torch.rand(2, 300, coords) * 0.8 + 0.1).to("cuda", dtype)
+    shapes = torch.tensor(BENCH_PYRAMID, device="cuda")
+    module = MultiscaleDeformableAttention(emb, hidden, levels, heads, points, "zeros", False).to("cuda", dtype)
+    gout = torch.randn(2, 300, emb).to("cuda", dtype)
+    calls = []
+    real = frontend.fused_value_proj_core
+    monkeypatch.setattr(frontend, "fused_value_proj_core", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+
+    def run(fused_value_proj):
+        monkeypatch.setenv("MSDA_B200_FUSED_VALUE_PROJ", "1" if fused_value_proj else "0")
+        i, q = (t.clone().requires_grad_(True) for t in (img, queries))
+        module.zero_grad()
+        out = module(i, shapes, q, ref_pts)
+        out.backward(gout)
+        return [out.detach(), i.grad, q.grad] + [p.grad.clone() for p in module.parameters()]
+
+    names = ["out", "grad_img", "grad_queries"] + ["grad " + n for n, _ in module.named_parameters()]
+    got = run(True)
+    assert len(calls) == 1
+    want = run(False)
+    assert len(calls) == 1
+    assert torch.equal(got[0], want[0])
+    eps = 2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -11
+    for name, a, b in zip(names[1:], got[1:], want[1:]):
+        b = to_np(b)
+        assert a.dtype == dtype
+        assert_close(to_np(a), b, 4 * eps, 4 * eps * np.abs(b).max(), name)
+
+    # not taken: inference, frozen bias, autocast
+    with torch.no_grad():
+        module(img, shapes, queries, ref_pts)
+    module.img_input_proj.bias.requires_grad_(False)
+    module(img, shapes, queries, ref_pts)
+    assert len(calls) == 1
