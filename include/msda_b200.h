@@ -103,7 +103,7 @@ const char *msda_last_error(void);
 /*
  * The library reads its measurement / test knobs (environment variables MSDA_B200_FORCE_GENERIC, _SLICES_PER_WAVE,
  * _PACE_SLACK, _WAVE_PACING, _FWD_VARIANT, _BWD_SPLIT, _SPLIT_SLOTS, _BWD_OWNER, _OWNER_ROWS, _OWNER_WORKERS,
- * _DET_VARIANT) once, at the first call that needs them, never on the launch path.  A process that changes one of them
+ * _DET_VARIANT, _BWD_DENSE, _DENSE_PF, _BWD_SHAPE, _CARVEOUT) once, at the first call that needs them, never on the launch path.  A process that changes one of them
  * afterwards calls this to have them read again.  No reference counterpart (the reference's only knob is Triton's
  * autotuner, kernels.py:259-265).
  */
