@@ -817,6 +817,11 @@ bool quant_backward_supported(const KernelArgs &a, int dtype) {
 }
 cudaError_t launch_backward_tiled_quant(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st) {
     if (!quant_backward_supported(a, dtype)) return cudaErrorNotSupported;
+    // same launch-shape rule as the atomic mode (see launch_backward_tiled): 12 warps x 168 registers for large problems
+    const long long tiles = (long long)a.B * a.H * ((a.Q + 3) / 4);
+    const int shape = tuning().bwd_shape >= 0 ? tuning().bwd_shape : (tiles >= 16LL * 16 * sm_count ? 1 : 0);
+    if (shape == 1)
+        return launch_tiled_t<float, 8, 16, false, 4, false, false, true, false, 0, 2, 384, 2>(a, sm_count, st);
     return launch_tiled_t<float, 8, 16, false, 4, false, false, true>(a, sm_count, st);
 }
 

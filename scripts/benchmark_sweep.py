@@ -4,7 +4,8 @@ query counts (``:13``), same three quantities -- forward ms (``:23-55``), forwar
 fresh ``rand_like`` gradient per run (``:71-107``) and peak extra memory of forward+backward (``:123-174``) -- and the
 same timing discipline as ``triton.testing.do_bench``: L2 flushed before every repetition, median of the reps.
 
-    python scripts/benchmark_sweep.py [--providers cuda torch] [--csv profiles/r1_benchmark_sweep.csv]
+    python scripts/benchmark_sweep.py [--providers cuda torch reference_triton] [--csv profiles/r2c_benchmark_sweep.csv]
+    python scripts/plot_sweep_svg.py profiles/r2c_benchmark_sweep.csv      # the three figures of benchmark.py:178-180 as SVG
 
 providers: ``cuda`` = this repository's kernels (public API), ``torch`` = the torch grid_sample route on the GPU (the
 reference's "Torch" line).  Prints a markdown table and optionally writes a CSV.
@@ -62,6 +63,17 @@ def main():
     ap.add_argument("--csv", default=None)
     ns = ap.parse_args()
     ops = {"cuda": triton_multiscale_deformable_attention, "torch": native_multiscale_deformable_attention}
+    if "reference_triton" in ns.providers:
+        # the UNMODIFIED reference package staged into baseline/_ref (scripts/stage_reference.py): its own Triton kernels,
+        # JIT-compiled for sm_100a -- the "Triton" line of the reference's published plots, on this GPU
+        sys.path.insert(0, str(ROOT))
+        import bench
+        ref, why = bench.load_reference_package()
+        if ref is None:
+            print(f"reference_triton unavailable: {why}", file=sys.stderr)
+            ns.providers = [p for p in ns.providers if p != "reference_triton"]
+        else:
+            ops["reference_triton"] = ref.triton_multiscale_deformable_attention
     flush = torch.empty(256 << 20, dtype=torch.int8, device="cuda")
     rows = []
     for n in QUERIES:
