@@ -59,7 +59,31 @@ def _check_buffer(buf: torch.Tensor, shape, like: torch.Tensor, what: str) -> No
                          f"{like.device}.")
 
 
+# Validated problem descriptions, keyed by everything they are derived from.  A decoder-sized forward kernel takes ~10 us, so
+# the per-call host work matters: rebuilding and re-validating the ctypes struct costs ~5 us, the lookup ~1.5 us.  The
+# structs are shared and never modified; `.ref` is the ready-made ctypes.byref() of the struct.
+_PROBLEMS: dict = {}
+_PROBLEMS_MAX = 512
+
+
+def _remember(key, prob: _lib.MsdaProblem) -> _lib.MsdaProblem:
+    prob.ref = ctypes.byref(prob)
+    if len(_PROBLEMS) >= _PROBLEMS_MAX:
+        _PROBLEMS.clear()
+    _PROBLEMS[key] = prob
+    return prob
+
+
 def _problem(img, img_shapes, pts, aw, padding_mode, align_corners) -> _lib.MsdaProblem:
+    key = (img.shape, img_shapes.shape, pts.shape, aw.shape, img.dtype, pts.dtype, aw.dtype, padding_mode,
+           bool(align_corners))
+    hit = _PROBLEMS.get(key)
+    if hit is not None:
+        return hit
+    return _remember(key, _build_problem(img, img_shapes, pts, aw, padding_mode, align_corners))
+
+
+def _build_problem(img, img_shapes, pts, aw, padding_mode, align_corners) -> _lib.MsdaProblem:
     if padding_mode not in _PAD_CODE:
         raise ValueError(f"`padding_mode` should be 'border' or 'zeros', but got {padding_mode!r}.")
     if img.dim() != 4 or pts.dim() != 6 or aw.dim() != 5 or img_shapes.dim() != 2:
@@ -141,7 +165,7 @@ def b200_multi_scale_deformable_attention_fwd(
     else:
         _check_buffer(out, (prob.B, prob.Q, prob.H, prob.D), img, "out")
     with _on_device_of(img) as stream:
-        rc = _lib.get_lib().msda_forward(_ptr(out), _ptr(img), _ptr(shapes), _ptr(pts), _ptr(aw), ctypes.byref(prob),
+        rc = _lib.get_lib().msda_forward(_ptr(out), _ptr(img), _ptr(shapes), _ptr(pts), _ptr(aw), prob.ref,
                                          stream)
     if rc:
         _lib.check(rc, "msda_forward")
@@ -189,10 +213,10 @@ def b200_multi_scale_deformable_attention_bwd(
     gaw = buffer(need_aw, pre[2], aw, "attention_weights_grad")
     lib = _lib.get_lib()
     with _on_device_of(img) as stream:
-        ws_bytes = int(lib.msda_backward_workspace_bytes(ctypes.byref(prob), flags))
+        ws_bytes = int(lib.msda_backward_workspace_bytes(prob.ref, flags))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=img.device) if ws_bytes else None
         rc = lib.msda_backward(_ptr(gimg), _ptr(gpts), _ptr(gaw), _ptr(gout), _ptr(img), _ptr(shapes), _ptr(pts),
-                               _ptr(aw), ctypes.byref(prob), flags, _ptr(ws), ws_bytes, stream)
+                               _ptr(aw), prob.ref, flags, _ptr(ws), ws_bytes, stream)
     if rc:
         _lib.check(rc, "msda_backward")
     return gimg, gpts, gaw
@@ -202,6 +226,15 @@ def b200_multi_scale_deformable_attention_bwd(
 # fused module core (frontend.py:253-289 of the reference in one kernel)
 # ---------------------------------------------------------------------------------------------------------------------
 def _module_problem(value, img_shapes, proj, ref, padding_mode, align_corners) -> _lib.MsdaProblem:
+    key = ("module", value.shape, img_shapes.shape, proj.shape, ref.shape, value.dtype, proj.dtype, ref.dtype,
+           padding_mode, bool(align_corners))
+    hit = _PROBLEMS.get(key)
+    if hit is not None:
+        return hit
+    return _remember(key, _build_module_problem(value, img_shapes, proj, ref, padding_mode, align_corners))
+
+
+def _build_module_problem(value, img_shapes, proj, ref, padding_mode, align_corners) -> _lib.MsdaProblem:
     if padding_mode not in _PAD_CODE:
         raise ValueError(f"`padding_mode` should be 'border' or 'zeros', but got {padding_mode!r}.")
     B, Npix, H, D = value.shape
@@ -223,10 +256,17 @@ def module_core_supported(value: torch.Tensor, proj: torch.Tensor, ref: torch.Te
         return False
     if not (value.dtype == proj.dtype == ref.dtype) or proj.dim() != 6 or ref.shape[-1] not in (2, 4):
         return False
-    B, Npix, H, D = value.shape
-    _, Q, _, L, K, _ = proj.shape
-    prob = _lib.MsdaProblem(B, Npix, H, D, Q, L, K, _DTYPE_CODE[value.dtype], 0, 0, 0)
-    return bool(_lib.get_lib().msda_module_supported(ctypes.byref(prob), int(ref.shape[-1])))
+    key = ("supported", value.shape, proj.shape, ref.shape[-1], value.dtype)
+    hit = _PROBLEMS.get(key)
+    if hit is None:
+        B, Npix, H, D = value.shape
+        _, Q, _, L, K, _ = proj.shape
+        prob = _lib.MsdaProblem(B, Npix, H, D, Q, L, K, _DTYPE_CODE[value.dtype], 0, 0, 0)
+        hit = bool(_lib.get_lib().msda_module_supported(ctypes.byref(prob), int(ref.shape[-1])))
+        if len(_PROBLEMS) >= _PROBLEMS_MAX:
+            _PROBLEMS.clear()
+        _PROBLEMS[key] = hit
+    return hit
 
 
 def module_core_supported_static(value: torch.Tensor, proj: torch.Tensor, ref: torch.Tensor) -> bool:
@@ -263,7 +303,7 @@ def b200_module_core_fwd(value, img_shapes, proj, ref, padding_mode, align_corne
     out = torch.empty((prob.B, prob.Q, prob.H, prob.D), dtype=value.dtype, device=value.device)
     with _on_device_of(value) as stream:
         rc = _lib.get_lib().msda_module_forward(_ptr(out), _ptr(value), _ptr(shapes), _ptr(proj), _ptr(ref),
-                                                int(ref.shape[-1]), ctypes.byref(prob), stream)
+                                                int(ref.shape[-1]), prob.ref, stream)
     if rc:
         _lib.check(rc, "msda_module_forward")
     return out
@@ -300,16 +340,16 @@ def b200_module_core_bwd(out_grad, value, img_shapes, proj, ref, padding_mode, a
     gref32 = torch.empty(ref.shape, dtype=torch.float32, device=value.device) if need_ref else None
     lib = _lib.get_lib()
     with _on_device_of(value) as stream:
-        ws_bytes = int(lib.msda_backward_workspace_bytes(ctypes.byref(prob), flags & (7 | _lib.BWD_VALUE_COLSUM)))
+        ws_bytes = int(lib.msda_backward_workspace_bytes(prob.ref, flags & (7 | _lib.BWD_VALUE_COLSUM)))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=value.device) if ws_bytes else None
         rc = lib.msda_module_backward(
             _ptr(gvalue), _ptr(gproj), _ptr(gref32), _ptr(gout), _ptr(value), _ptr(shapes), _ptr(proj), _ptr(ref),
-            int(ref.shape[-1]), ctypes.byref(prob), flags, _ptr(ws), ws_bytes, stream)
+            int(ref.shape[-1]), prob.ref, flags, _ptr(ws), ws_bytes, stream)
     if rc:
         _lib.check(rc, "msda_module_backward")
     gref = (gref32 if ref.dtype == torch.float32 else gref32.to(ref.dtype)) if need_ref else None
     if value_colsum:
-        off = int(lib.msda_module_colsum_offset(ctypes.byref(prob)))
+        off = int(lib.msda_module_colsum_offset(prob.ref))
         hd = value.shape[2] * value.shape[3]
         colsum = ws[off:off + 4 * hd].view(torch.float32).reshape(value.shape[2], value.shape[3])
         return gvalue, gproj, gref, colsum
@@ -327,14 +367,22 @@ def level_table(img_shapes: torch.Tensor, num_pixels: int) -> torch.Tensor:
     return table
 
 
+try:   # CPython's os.environ keeps the encoded variables in a plain dict
+    _ENV_DATA = os.environ._data
+    _VALIDATE_KEY = os.environ.encodekey("MSDA_B200_VALIDATE")
+except AttributeError:   # pragma: no cover
+    _ENV_DATA, _VALIDATE_KEY = None, None
+
+
 def _maybe_validate_shapes(shapes: torch.Tensor, num_pixels: int) -> None:
     """Like the reference (frontend.py:71-105), the hot path never checks that sum(h*w) equals the pyramid length --
     doing so needs a device->host sync.  MSDA_B200_VALIDATE=1 turns the check on (debugging aid): the level table is
     built on the device by the library and read back."""
-    if not _VALIDATE and "MSDA_B200_VALIDATE" not in os.environ:
-        return
-    if os.environ.get("MSDA_B200_VALIDATE", "0") == "0":
-        return
+    if not _VALIDATE:
+        # one dictionary lookup on the hot path (os.environ's own accessors encode the key on every call: ~1 us)
+        v = _ENV_DATA.get(_VALIDATE_KEY) if _ENV_DATA is not None else os.environ.get("MSDA_B200_VALIDATE")
+        if v is None or v in (b"0", "0"):
+            return
     table = level_table(shapes, num_pixels).cpu()
     if int(table[-1, 2]) != 1:
         raise ValueError(f"img_shapes describe {int(table[-1, 0])} pixels but img has {num_pixels}.")
