@@ -65,8 +65,15 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
                 raise RuntimeError(f"nvcc failed on {src.name}")
         return obj
 
-    with ThreadPoolExecutor(max_workers=min(8, len(sources))) as ex:
-        objs = list(ex.map(compile_one, sources))
+    # the translation units that instantiate the tuned kernel templates take 20-70 s each, the rest a few seconds: start
+    # the heavy ones first and use the cores there are
+    heavy = ("msda_fwd_tiled", "msda_fwd_module", "msda_bwd_tiled", "msda_bwd_dense", "msda_bwd_split", "msda_fwd_points",
+             "msda_bwd_module", "msda_bwd_shapes")
+    order = sorted(sources, key=lambda s: heavy.index(s.stem) if s.stem in heavy else len(heavy))
+    workers = max(1, min(os.cpu_count() or 8, 16, len(sources)))
+    with ThreadPoolExecutor(max_workers=workers) as ex:
+        done = dict(zip(order, ex.map(compile_one, order)))
+    objs = [done[s] for s in sources]
     if force or _stale(LIB, objs):
         cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *map(str, objs)]
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -14,11 +14,20 @@ cudaError_t launch_backward_generic(const KernelArgs &a, int dtype, int vec, int
 // does not fit so the caller falls through to the generic kernels.
 cudaError_t launch_forward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st);
 cudaError_t launch_backward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st);
+// pieces of the above that live in their own translation units (compile time): point counts other than 16 (forward),
+// more than 16 points per unit as sub-units (backward)
+cudaError_t launch_forward_tiled_points(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st);
+cudaError_t launch_backward_tiled_split(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st);
 
 // Fused module core (raw projection + reference points in, see msda_tiled.cuh).  cudaErrorNotSupported when the
 // problem is outside (fp32|fp16|bf16) x D in {32, 64} x L*K=16.
 cudaError_t launch_module_forward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st);
 cudaError_t launch_module_backward_tiled(const KernelArgs &a, int dtype, int sm_count, cudaStream_t st);
+
+// Experiments around the tuned fp32 backward, each in its own translation unit: n owner warps accumulating the coarsest
+// level in registers (msda_bwd_dense.cu) and the launch shapes 2..8 of MSDA_B200_BWD_SHAPE (msda_bwd_shapes.cu).
+cudaError_t launch_backward_dense(const KernelArgs &a, int sm_count, cudaStream_t st, int nown, int prefetch);
+cudaError_t launch_backward_shape_variant(const KernelArgs &a, int shape, int sm_count, cudaStream_t st);
 
 // Tuned backward with the coarse pyramid levels accumulated in tensor memory (msda_bwd_tmem.cu):
 // fp32, D == 32, L*K == 16, K == 4, grad_img requested.  cudaErrorNotSupported otherwise.
