@@ -11,12 +11,13 @@ template <int NOWN, int DPF> static cudaError_t launch_dense_t(const KernelArgs 
     return launch_tiled_t<float, 8, 16, false, 4, false, false, false, false, NOWN, DPF, 384>(a, sm_count, st);
 }
 cudaError_t launch_backward_dense(const KernelArgs &a, int sm_count, cudaStream_t st, int nown, int prefetch) {
-    const bool deep = prefetch >= 4;
-    if (nown >= 6) return deep ? launch_dense_t<6, 4>(a, sm_count, st) : launch_dense_t<6, 3>(a, sm_count, st);
-    if (nown >= 4) return deep ? launch_dense_t<4, 4>(a, sm_count, st) : launch_dense_t<4, 3>(a, sm_count, st);
-    if (nown == 3) return deep ? launch_dense_t<3, 4>(a, sm_count, st) : launch_dense_t<3, 3>(a, sm_count, st);
-    return deep ? launch_dense_t<2, 4>(a, sm_count, st) : launch_dense_t<2, 3>(a, sm_count, st);
+    // owners come in pairs (one per half of the 32 channels); 4 owners: two pairs, each taking every other unit
+    if (nown >= 4) {
+        if (prefetch >= 3) return launch_dense_t<4, 3>(a, sm_count, st);
+        return launch_dense_t<4, 2>(a, sm_count, st);
+    }
+    if (prefetch >= 3) return launch_dense_t<2, 3>(a, sm_count, st);
+    return launch_dense_t<2, 2>(a, sm_count, st);
 }
-
 
 }  // namespace msda

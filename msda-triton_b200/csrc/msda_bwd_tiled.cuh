@@ -36,93 +36,39 @@ template <int VEC, int LANES> __device__ __forceinline__ void red_add_row(float 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// DENSE (opt-in experiment, MSDA_B200_BWD_DENSE=n): register-resident accumulation of ONE coarse pyramid level by
+// DENSE (opt-in experiment, MSDA_B200_BWD_DENSE=2|4): register-resident accumulation of ONE coarse pyramid level by
 // specialised "owner" warps.
 //
 // The backward is bound by the SM's row-add injection into L2 (5.8 clk per 128-byte row).  Earlier attempts to merge row
 // adds on chip all had the worker warps hand their records to an accumulator through shared or tensor memory and lost to
 // the hand-off (LSU queueing behind the reds, tensor-memory round trips).  Here nothing is handed over: the last NOWN
 // warps of the CTA do not take warp tiles at all; they walk the SAME units of the CTA's range a second time, read only
-// the 176 bytes a unit needs for one level (grad_out row: one coalesced 4-byte load per lane = lane per channel; the
-// level's 4 points and weights: three warp-uniform 16-byte loads, DPF units ahead), recompute the level's taps with the
-// same locate() as the workers and accumulate  acc[cell] += (attention x bilinear weight) * grad_out[channel]  in 64
-// REGISTERS per lane (lane = channel, register = cell of the level: levels of at most 64 cells, 8x8 on the benchmark
-// pyramid).  A register file has no dynamic index, so the add goes through a 64-way indirect branch (brx.idx; the
-// x-neighbour corner rides along as cell + 1 under a warp-uniform predicate: 8 branches per unit).  The owners flush their
-// 64 rows with one scalar red per lane and row when the CTA's range leaves a (b,h) slice, and the workers skip the row
-// adds of that level: a quarter of the backward's `red` sectors never leave the SM.
-// Eligibility (host): fp32, D == 32, L == 4, K == 4, grad_img requested; the level is picked on the device (largest level
-// with h*w <= 64); without one the owners only keep the wave barriers company.  12 warps x 168 registers (see
-// launch_dense_t).
-// MEASURED (B200, bench shape, profiles/r2_dense_backward.md): correct (tests/test_dense_backward_gpu.py) and SLOWER --
-// 1.75 / 1.29 / 1.10 / 1.01 ms with 2 / 3 / 4 / 6 owners against 0.48 ms plain: the owners are the critical path at
-// ~3.5k clk per unit whatever the prefetch depth and whether or not the four taps are resolved ahead of the adds; a lone
-// warp pays each of its ~16 taken branches per unit (8 indirect) in full, there is no second warp on the same accumulators
-// to hide them.  The branch-free alternative (lane = cell, 64 FFMA per unit against a per-lane weight) needs the whole
-// grad_out row replicated in every lane: 44 registers per unit in flight, and the ~1.2k clk LSU latency under the reds
-// asks for four units in flight.  Kept as a recorded experiment; default off.
+// the 112 bytes a unit needs for one level and half of the channels (warp-uniform 16-byte loads, DPF units in flight),
+// and accumulate the level DENSELY in registers: lane = cell (two cells per lane: levels of at most 64 cells, 8x8 on the
+// benchmark pyramid), 16 channels per owner, weight(cell) = sum over the level's 4 points of attention weight x
+// tent(x - cell_x) x tent(y - cell_y) -- the bilinear corner weights written per cell, so that no register is indexed
+// dynamically and nothing branches (dense_owner_wave below).  The owners flush their rows when the CTA's range leaves a
+// (b,h) slice, and the workers skip the row adds of that level: a quarter of the backward's `red` sectors never leave
+// the SM.  Eligibility (host): fp32, D == 32, L == 4, K == 4, grad_img requested; the level is picked on the device
+// (largest level with h*w <= 64); without one the owners only keep the wave barriers company.  12 warps x 168 registers.
+// MEASURED (B200, bench shape, profiles/r2_dense_backward.md): correct (tests/test_dense_backward_gpu.py) and SLOWER than
+// the plain kernel (0.47 ms): 2.05 / 1.07 ms with 2 / 4 owners -- time ~ 1 / owners at ~1.9k clk per unit, i.e. one trip
+// through the LSU per unit: under the reds every load takes that long, a unit in flight costs 28 registers, and 64
+// accumulators' worth of register file leaves room for two (three spill: 1.29 ms).  The first version of this experiment
+// (lane = channel, register = cell, the add dispatched through a 64-way brx.idx; commit 9e100fd) needed only 13
+// registers per unit in flight and hid the loads, but paid ~3.5k clk per unit for its 16 taken branches: 1.75 / 1.10 / 1.01
+// ms with 2 / 4 / 6 owners.  And owner warps are not free: with the owners idle the kernel slows down ~ 1 / workers below
+// 12 warps.  Kept as a recorded experiment; default off.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kDenseCells = 64;
 constexpr unsigned kPackDenseBit = 1u << 30;   // TileTap::pack: the point's level is accumulated by the owner warps
 
-// acc[cell] += sa * g (if pa);  acc[cell + 1] += sb * g (if pb).  cell, pa, pb, sa, sb are warp-uniform, g is the lane's
-// channel.  Written as ONE brx.idx over a 64-entry target list: nvcc lowers a C++ switch of this size to a five-deep tree
-// of compare-and-branch with two-way BRX leaves, and sinks the operand arithmetic into every case.
-#define MSDA_DENSE_ACC8(b) "+f"(acc[b]), "+f"(acc[b + 1]), "+f"(acc[b + 2]), "+f"(acc[b + 3]), "+f"(acc[b + 4]), \
-                           "+f"(acc[b + 5]), "+f"(acc[b + 6]), "+f"(acc[b + 7])
-#define MSDA_DENSE_CASE(k, k1)                                   \
-    "DC" #k ":\n"                                                \
-    "@pa fma.rn.f32 %" #k ", %66, %68, %" #k ";\n"                \
-    "@pb fma.rn.f32 %" #k1 ", %67, %68, %" #k1 ";\n"              \
-    "bra.uni DCEND;\n"
-__device__ __forceinline__ void dense_add_pair(float (&acc)[kDenseCells], int cell, bool pa, float sa, bool pb, float sb,
-                                               float g) {
-    static_assert(kDenseCells == 64, "the target list below has 64 entries");
-    const unsigned idx = min((unsigned)cell, 63u);
-    const unsigned preds = (pa ? 1u : 0u) | ((pb && idx < 63u) ? 2u : 0u);
-    asm volatile(
-        "{\n"
-        ".reg .pred pa, pb;\n"
-        ".reg .b32 t;\n"
-        "and.b32 t, %65, 1;\n"
-        "setp.ne.b32 pa, t, 0;\n"
-        "and.b32 t, %65, 2;\n"
-        "setp.ne.b32 pb, t, 0;\n"
-        "DCT: .branchtargets DC0, DC1, DC2, DC3, DC4, DC5, DC6, DC7, DC8, DC9, DC10, DC11, DC12, DC13, DC14, DC15, DC16, "
-        "DC17, DC18, DC19, DC20, DC21, DC22, DC23, DC24, DC25, DC26, DC27, DC28, DC29, DC30, DC31, DC32, DC33, DC34, DC35, "
-        "DC36, DC37, DC38, DC39, DC40, DC41, DC42, DC43, DC44, DC45, DC46, DC47, DC48, DC49, DC50, DC51, DC52, DC53, DC54, "
-        "DC55, DC56, DC57, DC58, DC59, DC60, DC61, DC62, DC63;\n"
-        "brx.idx.uni %64, DCT;\n"
-        MSDA_DENSE_CASE(0, 1) MSDA_DENSE_CASE(1, 2) MSDA_DENSE_CASE(2, 3) MSDA_DENSE_CASE(3, 4) MSDA_DENSE_CASE(4, 5)
-        MSDA_DENSE_CASE(5, 6) MSDA_DENSE_CASE(6, 7) MSDA_DENSE_CASE(7, 8) MSDA_DENSE_CASE(8, 9) MSDA_DENSE_CASE(9, 10)
-        MSDA_DENSE_CASE(10, 11) MSDA_DENSE_CASE(11, 12) MSDA_DENSE_CASE(12, 13) MSDA_DENSE_CASE(13, 14)
-        MSDA_DENSE_CASE(14, 15) MSDA_DENSE_CASE(15, 16) MSDA_DENSE_CASE(16, 17) MSDA_DENSE_CASE(17, 18)
-        MSDA_DENSE_CASE(18, 19) MSDA_DENSE_CASE(19, 20) MSDA_DENSE_CASE(20, 21) MSDA_DENSE_CASE(21, 22)
-        MSDA_DENSE_CASE(22, 23) MSDA_DENSE_CASE(23, 24) MSDA_DENSE_CASE(24, 25) MSDA_DENSE_CASE(25, 26)
-        MSDA_DENSE_CASE(26, 27) MSDA_DENSE_CASE(27, 28) MSDA_DENSE_CASE(28, 29) MSDA_DENSE_CASE(29, 30)
-        MSDA_DENSE_CASE(30, 31) MSDA_DENSE_CASE(31, 32) MSDA_DENSE_CASE(32, 33) MSDA_DENSE_CASE(33, 34)
-        MSDA_DENSE_CASE(34, 35) MSDA_DENSE_CASE(35, 36) MSDA_DENSE_CASE(36, 37) MSDA_DENSE_CASE(37, 38)
-        MSDA_DENSE_CASE(38, 39) MSDA_DENSE_CASE(39, 40) MSDA_DENSE_CASE(40, 41) MSDA_DENSE_CASE(41, 42)
-        MSDA_DENSE_CASE(42, 43) MSDA_DENSE_CASE(43, 44) MSDA_DENSE_CASE(44, 45) MSDA_DENSE_CASE(45, 46)
-        MSDA_DENSE_CASE(46, 47) MSDA_DENSE_CASE(47, 48) MSDA_DENSE_CASE(48, 49) MSDA_DENSE_CASE(49, 50)
-        MSDA_DENSE_CASE(50, 51) MSDA_DENSE_CASE(51, 52) MSDA_DENSE_CASE(52, 53) MSDA_DENSE_CASE(53, 54)
-        MSDA_DENSE_CASE(54, 55) MSDA_DENSE_CASE(55, 56) MSDA_DENSE_CASE(56, 57) MSDA_DENSE_CASE(57, 58)
-        MSDA_DENSE_CASE(58, 59) MSDA_DENSE_CASE(59, 60) MSDA_DENSE_CASE(60, 61) MSDA_DENSE_CASE(61, 62)
-        MSDA_DENSE_CASE(62, 63) MSDA_DENSE_CASE(63, 63)
-        "DCEND:\n"
-        "}\n"
-        : MSDA_DENSE_ACC8(0), MSDA_DENSE_ACC8(8), MSDA_DENSE_ACC8(16), MSDA_DENSE_ACC8(24), MSDA_DENSE_ACC8(32),
-          MSDA_DENSE_ACC8(40), MSDA_DENSE_ACC8(48), MSDA_DENSE_ACC8(56)
-        : "r"(idx), "r"(preds), "f"(sa), "f"(sb), "f"(g));
-}
-#undef MSDA_DENSE_CASE
-#undef MSDA_DENSE_ACC8
-
-// What an owner warp holds of one unit while its loads are in flight.
+// What an owner warp holds of one unit while its loads are in flight: its half of the grad_out row (16 channels), the
+// dense level's 4 sampling points (x, y) and their attention weights -- all loaded with warp-uniform addresses.
 struct DenseSlot {
-    float g;          // grad_out[u, lane]
-    float4 p0, p1;    // the dense level's 4 sampling points (x, y)
-    float4 w;         // their attention weights
+    float4 g[4];
+    float4 p0, p1;
+    float4 w;
 };
 
 // Position of an owner warp in the flattened units i = 4 tile + query slot of the CTA's tile range: (b,h) slice `bh` starts
@@ -139,7 +85,12 @@ struct DenseCursor {
     }
 };
 
-// One wave of an owner warp: owner `o` of `nown` takes the flat units i = 4 t_begin + o, + nown, ... below 4 t_end.
+// One wave of an owner warp.  LANE = CELL: lane l owns cells l and l + 32 of the level and accumulates, for its 16
+// channels (owner o: channels 16 (o & 1) ..), acc[cell][channel] += weight(cell) * grad_out[channel], where weight(cell) is
+// the sum over the level's 4 points of  attention weight x tent(x - cell_x) x tent(y - cell_y)  -- the bilinear corner
+// weights written per CELL instead of per corner (tent(d) = max(0, 1 - |d|); border padding: on the clamped coordinate,
+// which folds clamped twin corners exactly as the row adds would).  No register is indexed dynamically and nothing
+// branches: ~120 instructions of weights + 32 FFMA per unit.  Owners with the same (o & 1) split the units between them.
 template <bool BORDER, int DPF>
 __device__ __forceinline__ void dense_owner_wave(const KernelArgs &a, const Level lv, const int level, const int t_begin,
                                                  const int t_end, const int tiles_per_bh, const int o, const int nown,
@@ -152,14 +103,22 @@ __device__ __forceinline__ void dense_owner_wave(const KernelArgs &a, const Leve
     const int cells = lv.h * lv.w;
     const int slice_len = tiles_per_bh * G;
     const size_t row_stride = (size_t)a.H * a.D;
+    const int ch0 = (o & 1) * 16;                 // this owner's channels
+    const int step = nown >> 1, phase = o >> 1;   // ... and its share of the units
 
-    float acc[kDenseCells];
+    // this lane's two cells as (x, y); a cell beyond the level sits far away from every coordinate (weight 0)
+    const int cA = lane, cB = lane + 32;
+    const float fxA = cA < cells ? (float)(cA % lv.w) : 1.0e30f, fyA = cA < cells ? (float)(cA / lv.w) : 1.0e30f;
+    const float fxB = cB < cells ? (float)(cB % lv.w) : 1.0e30f, fyB = cB < cells ? (float)(cB / lv.w) : 1.0e30f;
+    const float wf = (float)lv.w, hf = (float)lv.h, wm1 = (float)(lv.w - 1), hm1 = (float)(lv.h - 1);
+
+    float accA[16], accB[16];
 #pragma unroll
-    for (int c = 0; c < kDenseCells; ++c) acc[c] = 0.0f;
+    for (int c = 0; c < 16; ++c) accA[c] = accB[c] = 0.0f;
     int acc_bh = -1;
 
     DenseCursor cur, pre;   // consume / fetch
-    cur.i = t_begin * G + o;
+    cur.i = t_begin * G + phase;
     cur.bh = t_begin / tiles_per_bh;
     cur.start = cur.bh * slice_len;
     cur.settle(slice_len);
@@ -168,94 +127,109 @@ __device__ __forceinline__ void dense_owner_wave(const KernelArgs &a, const Leve
     // loads of the unit under the fetch cursor (nothing when it is past the end or on a padding query), then one step
     auto fetch = [&]() {
         DenseSlot s;
-        s.g = 0.0f;
-        s.p0 = s.p1 = s.w = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        const float4 zero = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        s.g[0] = s.g[1] = s.g[2] = s.g[3] = s.p0 = s.p1 = s.w = zero;
         const int q = pre.i - pre.start;
         if (pre.i < end && q < a.Q) {   // warp-uniform
             const int b = pre.bh / a.H, h = pre.bh - b * a.H;
             const size_t u = ((size_t)b * a.Q + q) * a.H + h;
-            s.g = __ldg(gout + u * 32 + lane);
+            const float4 *gp = reinterpret_cast<const float4 *>(gout + u * 32 + ch0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s.g[k] = __ldg(gp + k);
             const float4 *pp = reinterpret_cast<const float4 *>(pts + (u * 16 + level * 4) * 2);
             s.p0 = __ldg(pp);
             s.p1 = __ldg(pp + 1);
             s.w = __ldg(reinterpret_cast<const float4 *>(aw + u * 16 + level * 4));
         }
-        pre.i += nown;
+        pre.i += step;
         pre.settle(slice_len);
         return s;
     };
 
-    // DPF units in flight; the slot a unit leaves is refilled AFTER the unit has been accumulated, so that the registers
-    // of the unit being worked on and of the new loads are never live together (64 accumulators + the slots + the point
-    // loop's temporaries have to fit 128 registers: a spilled slot would wait for its loads at the spill)
+    // DPF units in flight; the slot a unit leaves is refilled AFTER the unit has been accumulated
     DenseSlot ring[DPF];
 #pragma unroll
     for (int k = 0; k < DPF; ++k) ring[k] = fetch();
 
-    for (;; cur.i += nown) {
+    // one unit: flush on a slice change, accumulate the unit held in `slot`, refill `slot`; true when the range is done.
+    // The ring is walked with static indices (the loop below is unrolled over it): rotating the slots through ring[0]
+    // would keep two copies of a slot alive across the moves.
+    auto unit = [&](DenseSlot &slot) -> bool {
         cur.settle(slice_len);
         const bool done = cur.i >= end;
         const bool valid = !done && cur.i - cur.start < a.Q;   // else: padding query, nothing to add
         const int bh = done ? -2 : cur.bh;
         if ((done || valid) && bh != acc_bh) {
-            // the range leaves slice acc_bh (or ends): one scalar row add per lane (= channel) and cell.  ONE flush site.
+            // the range leaves slice acc_bh (or ends): the lane's two rows, 16 channels each, as four row adds per cell
             if (acc_bh >= 0) {
                 const int b = acc_bh / a.H, h = acc_bh - b * a.H;
-                float *__restrict__ dst = gimg + ((size_t)b * a.Npix * a.H + h) * a.D + (size_t)lv.off * row_stride + lane;
+                float *__restrict__ base = gimg + ((size_t)b * a.Npix * a.H + h) * a.D + (size_t)lv.off * row_stride + ch0;
+                if (cA < cells) {
+                    float *dst = base + (size_t)cA * row_stride;
 #pragma unroll
-                for (int c = 0; c < kDenseCells; ++c) {
-                    if (c < cells) red_add_v1(dst, acc[c]);
-                    dst += row_stride;
-                    acc[c] = 0.0f;
+                    for (int k = 0; k < 4; ++k) red_add_v4(dst + 4 * k, accA[4 * k], accA[4 * k + 1], accA[4 * k + 2], accA[4 * k + 3]);
+                }
+                if (cB < cells) {
+                    float *dst = base + (size_t)cB * row_stride;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) red_add_v4(dst + 4 * k, accB[4 * k], accB[4 * k + 1], accB[4 * k + 2], accB[4 * k + 3]);
                 }
             }
+#pragma unroll
+            for (int c = 0; c < 16; ++c) accA[c] = accB[c] = 0.0f;
             acc_bh = bh;
         }
-        if (done) break;
-        const float g = ring[0].g;
-        float px0 = ring[0].p0.x, py0 = ring[0].p0.y, px1 = ring[0].p0.z, py1 = ring[0].p0.w;
-        float px2 = ring[0].p1.x, py2 = ring[0].p1.y, px3 = ring[0].p1.z, py3 = ring[0].p1.w;
-        float fw0 = ring[0].w.x, fw1 = ring[0].w.y, fw2 = ring[0].w.z, fw3 = ring[0].w.w;
+        if (done) return true;
+        const DenseSlot &s = slot;
+        if (valid) {
+            // the four points one after the other (not unrolled: interleaving them costs ~40 registers of temporaries, which
+            // the prefetched units need); they rotate through (px0, py0, fw0)
+            float px0 = s.p0.x, py0 = s.p0.y, px1 = s.p0.z, py1 = s.p0.w, px2 = s.p1.x, py2 = s.p1.y, px3 = s.p1.z, py3 = s.p1.w;
+            float fw0 = s.w.x, fw1 = s.w.y, fw2 = s.w.z, fw3 = s.w.w;
+            float wA = 0.0f, wB = 0.0f;
+#pragma unroll 1
+            for (int p = 0; p < 4; ++p) {
+                // the same un-normalisation, in the same operation order, as locate()
+                float x = align ? mul_rn(px0, wm1) : sub_rn(mul_rn(px0, wf), 0.5f);
+                float y = align ? mul_rn(py0, hm1) : sub_rn(mul_rn(py0, hf), 0.5f);
+                float wp = fw0;
+                if constexpr (BORDER) {
+                    // a non-finite coordinate gives NaN corner weights on the clamped cell (x - floor(x) is NaN): carry
+                    // that over as a NaN attention weight -- (x - x) is 0 for finite x, NaN otherwise
+                    wp = wp + __fsub_rn(x, x) + __fsub_rn(y, y);
+                    x = fminf(fmaxf(x, 0.0f), wm1);
+                    y = fminf(fmaxf(y, 0.0f), hm1);
+                }
+                const float tA = fmaxf(0.0f, 1.0f - fabsf(x - fxA)) * fmaxf(0.0f, 1.0f - fabsf(y - fyA));
+                const float tB = fmaxf(0.0f, 1.0f - fabsf(x - fxB)) * fmaxf(0.0f, 1.0f - fabsf(y - fyB));
+                // only the cells the point touches take its weight (a NaN / Inf weight must not reach the others)
+                if (tA > 0.0f) wA = fmaf(wp, tA, wA);
+                if (tB > 0.0f) wB = fmaf(wp, tB, wB);
+                px0 = px1, py0 = py1, fw0 = fw1;
+                px1 = px2, py1 = py2, fw1 = fw2;
+                px2 = px3, py2 = py3, fw2 = fw3;
+            }
+            const float gch[16] = {s.g[0].x, s.g[0].y, s.g[0].z, s.g[0].w, s.g[1].x, s.g[1].y, s.g[1].z, s.g[1].w,
+                                   s.g[2].x, s.g[2].y, s.g[2].z, s.g[2].w, s.g[3].x, s.g[3].y, s.g[3].z, s.g[3].w};
+            // untouched cells (weight 0) are skipped: 0 x Inf of a non-finite grad_out must not poison them
+            if (wA != 0.0f) {
 #pragma unroll
-        for (int k = 0; k + 1 < DPF; ++k) ring[k] = ring[k + 1];
-        if (!valid) {
-            ring[DPF - 1] = fetch();
-            continue;
-        }
-        // All four taps are resolved FIRST (four independent dependency chains the warp can interleave), then the eight
-        // (point, row pair) adds follow back to back: a lone warp pays every taken branch and every dependent result in
-        // full, and with the arithmetic between the branches a unit took ~3.6k clk.
-        const float pxs[4] = {px0, px1, px2, px3}, pys[4] = {py0, py1, py2, py3}, fws[4] = {fw0, fw1, fw2, fw3};
-        int cell[8];
-        bool pa[8], pb[8];
-        float sa[8], sb[8];
+                for (int c = 0; c < 16; ++c) accA[c] = fmaf(wA, gch[c], accA[c]);
+            }
+            if (wB != 0.0f) {
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            const Tap<float> t = locate<float>(pxs[p], pys[p], lv, BORDER, align);
-            const int c00 = t.row00 - lv.off;
-            const int dys = t.pack & kPackDyMask;                 // 0 or w: cell step to the y1 corners
-            const bool two = (t.pack >> kPackDxBit) & 1;          // x1 is a different cell than x0
-            const unsigned mask = BORDER ? 0xFu : (((unsigned)t.pack >> kPackMaskShift) & 0xFu);
-            const float dx = t.dx, dy = t.dy;
-            // same corner weights, in the same operation order, as the workers' (bw[] in the kernel below)
-            const float b1 = (1.0f - dy) * dx, b0 = (1.0f - dy) - b1;
-            const float b3 = dy * dx, b2 = dy - b3;
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                // x-neighbours of row r: cells c and c + 1 when `two`, else both corners land on cell c (clamped)
-                const bool vlo = (mask >> (2 * r)) & 1u, vhi = (mask >> (2 * r + 1)) & 1u;
-                const float slo = fws[p] * (r ? b2 : b0), shi = fws[p] * (r ? b3 : b1);
-                pa[2 * p + r] = vlo || (!two && vhi);
-                pb[2 * p + r] = two && vhi;
-                sa[2 * p + r] = (vlo ? slo : 0.0f) + ((!two && vhi) ? shi : 0.0f);
-                sb[2 * p + r] = shi;
-                cell[2 * p + r] = c00 + (r ? dys : 0);
+                for (int c = 0; c < 16; ++c) accB[c] = fmaf(wB, gch[c], accB[c]);
             }
         }
+        slot = fetch();
+        cur.i += step;
+        return false;
+    };
+    for (bool done = false; !done;) {
 #pragma unroll
-        for (int n = 0; n < 8; ++n)
-            if (pa[n] || pb[n]) dense_add_pair(acc, cell[n], pa[n], sa[n], pb[n], sb[n], g);
-        ring[DPF - 1] = fetch();
+        for (int k = 0; k < DPF; ++k) {
+            if (!done) done = unit(ring[k]);
+        }
     }
 }
 

@@ -33,7 +33,7 @@ void read_env() {
     t.l1_keep_kb = env_int("MSDA_B200_L1_KEEP_KB", 100);
     t.bwd_agg = env_int("MSDA_B200_BWD_AGG", -1);
     t.bwd_dense = env_int("MSDA_B200_BWD_DENSE", -1);
-    t.dense_prefetch = env_int("MSDA_B200_DENSE_PF", 3);
+    t.dense_prefetch = env_int("MSDA_B200_DENSE_PF", 2);
     t.bwd_shape = env_int("MSDA_B200_BWD_SHAPE", -1);
     t.carveout = env_int("MSDA_B200_CARVEOUT", -1);
     t.det_variant = env_int("MSDA_B200_DET_VARIANT", -1);

@@ -20,7 +20,7 @@ struct Tuning {
                                //                                are gathered with no-allocate loads (-1: never)
     int bwd_agg = -1;          // MSDA_B200_BWD_AGG=0|1        : pair aggregation of neighbouring queries' row adds (experiment, default off)
     int bwd_dense = -1;        // MSDA_B200_BWD_DENSE=n        : owner warps of the dense-level backward (experiment, default off)
-    int dense_prefetch = 3;    // MSDA_B200_DENSE_PF=3|4       : units an owner warp keeps in flight
+    int dense_prefetch = 2;    // MSDA_B200_DENSE_PF=2|3       : units an owner warp keeps in flight (3 spills)
     int bwd_shape = -1;        // MSDA_B200_BWD_SHAPE=0..5     : fp32 backward launch shape: 16 warps x 128 regs | 12 x 168 | experiments
                                //                                (default: 12 x 168 for problems with many warp tiles per warp)
     int carveout = -1;         // MSDA_B200_CARVEOUT=0..100    : preferred shared-memory carve-out of the tuned kernels (experiment)

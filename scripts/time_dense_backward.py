@@ -32,7 +32,7 @@ def timeit(fn, reps=25, warm=4):
     return round(ts[len(ts) // 2], 4)
 
 
-variants = [("0", "3", sh) for sh in "013452"] + [(n, "3", "0") for n in ("4", "6")]
+variants = [("0", "2", "0"), ("0", "2", "1")] + [(n, pf, "1") for n in ("2", "4") for pf in ("2", "3")]
 for name in sys.argv[1:] or ["bench_q10k_border", "bench_q10k_zeros", "readme_q900_zeros", "detr_encoder_zeros"]:
     B, Q, H, D, pyr, Kp, pm, ac = bench.WORKLOADS[name]
     t, s = bench.make_inputs(name, 0, device="cuda")
