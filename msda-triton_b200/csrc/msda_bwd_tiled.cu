@@ -133,6 +133,8 @@ cudaError_t launch_backward_tiled(const KernelArgs &a, int dtype, int sm_count, 
         }
         if (a.D == 64) return launch_tiled_t<float, 16, 16>(a, sm_count, st);
     } else if (dtype == 1) {
+        // (16-bit storage keeps the 16 warps: at 12 x 168 the bf16 backward measured -0.6 % on the bench shape, +0.7 % on the
+        // DETR encoder, +1 % at B = 16 -- MSDA_TIME_DTYPE=bf16 scripts/time_bwd_shapes.py)
         if (a.D == 32) return launch_tiled_t<__half, 8, 16, false, 4>(a, sm_count, st);
         if (a.D == 64) return launch_tiled_t<__half, 16, 16, false, 4>(a, sm_count, st);
     } else if (dtype == 2) {

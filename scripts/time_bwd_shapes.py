@@ -1,5 +1,6 @@
 """Backward launch shape (MSDA_B200_BWD_SHAPE): 16 warps x 128 registers (0) against 12 warps x 168 registers (1) and the
-variants with the tap exchange issued one batch ahead (3, 4); cold L2, medians of 25, alternating order."""
+variants with the tap exchange issued one batch ahead (3, 4); cold L2, medians of 25, alternating order.
+MSDA_TIME_DTYPE=bf16|f16 times the 16-bit-storage backward (incl. its fp32 scratch zero-fill and rounding pass)."""
 import json
 import os
 import sys
@@ -34,6 +35,7 @@ def timeit(fn, reps, warm=3):
     return round(ts[len(ts) // 2], 4)
 
 
+DTYPE = {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16}[os.environ.get("MSDA_TIME_DTYPE", "f32")]
 shapes = sys.argv[1].split(",") if len(sys.argv) > 1 else ["0", "1"]
 names = sys.argv[2:] or ["bench_q10k_border", "bench_q10k_zeros", "detr_encoder_zeros", "detr_encoder_local_zeros",
                          "readme_q900_zeros", "decoder_q900_detr_pyramid", "encoder_b16_zeros", "train_b64_encoder_zeros"]
@@ -50,6 +52,7 @@ for name in names:
              "aw": torch.rand(B, Q, H, len(pyr), Kp, device="cuda", generator=g),
              "go": torch.rand(B, Q, H, D, device="cuda", generator=g)}
         s = torch.tensor(pyr, device="cuda")
+    t = {k: v.to(DTYPE) for k, v in t.items()}
     reps = 7 if B >= 16 else 25
     row = {}
     for rnd in range(2):                      # two rounds, alternating, to see the run-to-run spread
